@@ -1,0 +1,181 @@
+/*
+ * srb200.h — C ABI of libsrb200.so, the B200 (sm_100a) kernel library behind the SRModel
+ * plugin API of george-gca/sr-pytorch-lightning.
+ *
+ * The reference has no FFI of its own: its hot path is Python calling torch.nn modules
+ * (SURVEY.md §8b).  The entry points below are what a binding for that path replaces; each
+ * one cites the reference call site(s) it stands in for.  Rules of the ABI:
+ *   - plain pointers and sizes only (device pointers come from tensor.data_ptr(); the stream is
+ *     a cudaStream_t passed as void*); no torch types; POD structs;
+ *   - every function returns 0 on success, non-zero on error; srb_last_error() gives the text
+ *     (thread-local); nothing throws or exits across the boundary;
+ *   - every kernel is launched on the given stream, never synchronises the host and never
+ *     allocates device memory, so every call is CUDA-graph capturable;
+ *   - activations are NHWC ("pixel-major") with an explicit channel stride `cs` (elements per
+ *     pixel) and channel offset `co`, which is how RDN's torch.cat (models/rdn.py:21,108) is
+ *     eliminated: a dense block is one [N,H,W,576] buffer and every conv reads a channel prefix
+ *     and writes a channel slice of it.
+ */
+#ifndef SRB200_H
+#define SRB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRB_ABI_VERSION 1
+
+typedef struct srb_ctx srb_ctx;
+
+/* element type of activation tensors */
+enum { SRB_F32 = 0, SRB_BF16 = 1 };
+
+/* conv epilogue flags:  v = acc (+bias); RELU; v *= scale; MASK: v = mask>0 ? v : 0;
+ *                       RESIDUAL: v += residual; store (optionally pixel-shuffled); COLSUM */
+enum {
+  SRB_RELU     = 1,   /* nn.ReLU(True) after the conv (common.py:46,89; rcan.py:36,46; rdn.py:16) */
+  SRB_RESIDUAL = 2,   /* `res += x` (common.py:107; rcan.py:54,73,122; edsr.py:47; rdn.py:40,109) */
+  SRB_MASK     = 4,   /* ReLU backward: zero where the saved post-ReLU activation is <= 0          */
+  SRB_COLSUM   = 8,   /* per-channel sums of the stored values: CALayer's AdaptiveAvgPool2d
+                         numerator (rcan.py:14,25) in forward, bias gradients in backward          */
+  SRB_OUT2     = 16   /* also store the result into a second tensor (RDN: LFF output feeds both the
+                         next RDB and the GFF concat buffer, rdn.py:104-108)                        */
+};
+
+/* weight packings produced by srb_pack_weight */
+enum {
+  SRB_PACK_SIMT = 0,  /* fp32 [kh][kw][Cin][Cout]                        (CUDA-core kernels)       */
+  SRB_PACK_UMMA = 1   /* bf16 [Cin/64][kw][kh][Cout][64], K-major 128-B rows (tcgen05 kernels)     */
+};
+enum { SRB_PACK_FWD = 0, SRB_PACK_DGRAD = 1 };
+
+/* kernel family selection */
+enum { SRB_BACKEND_AUTO = 0, SRB_BACKEND_SIMT = 1, SRB_BACKEND_UMMA = 2 };
+
+typedef struct srb_conv_desc {
+  int32_t N, H, W;          /* conv input == conv output spatial size (stride 1, padding k/2)    */
+  int32_t Cin, Cout, ksize; /* ksize odd; tcgen05 path: 1 or 3                                     */
+  int32_t dtype;            /* SRB_F32 / SRB_BF16 for x, y, residual, mask, y2                      */
+  int32_t flags;
+  float   scale;            /* res_scale (common.py:106); 1.0 when unused                          */
+  int32_t shuffle;          /* 0, or r (2|3): fold nn.PixelShuffle(r) (common.py:133; rdn.py:87-92)
+                               into the store: y is [N, H*r, W*r, Cout/(r*r)]                      */
+  int32_t colsum_groups;    /* with SRB_COLSUM: 1 -> colsum[Cout]; N -> colsum[N][Cout]            */
+  int32_t backend;
+  int32_t x_cs, x_co;       /* channel stride / offset (elements) of x                             */
+  int32_t y_cs, y_co;       /* ... of y (in the shuffled tensor when shuffle != 0)                  */
+  int32_t r_cs, r_co;       /* ... of residual (same pixel grid as y)                               */
+  int32_t m_cs, m_co;       /* ... of mask     (same pixel grid as y)                               */
+  int32_t y2_cs, y2_co;     /* ... of y2                                                            */
+} srb_conv_desc;
+
+typedef struct srb_wgrad_desc {
+  int32_t N, H, W;
+  int32_t Cin, Cout, ksize;
+  int32_t dtype;            /* of x and gy */
+  int32_t accumulate;       /* 0: overwrite dw/dbias, 1: += (gradient accumulation)                */
+  int32_t shuffle;          /* r if gy is given in the un-shuffled (i,j,c') channel order          */
+  int32_t backend;
+  int32_t x_cs, x_co;
+  int32_t g_cs, g_co;
+  float   alpha;            /* dw = alpha * (x (*) gy): res_scale of common.py:106 on the weight grad */
+} srb_wgrad_desc;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int  srb_abi_version(void);
+const char* srb_last_error(void);
+int  srb_create(int device, srb_ctx** out);
+int  srb_destroy(srb_ctx* ctx);
+int  srb_num_sms(const srb_ctx* ctx);
+
+/* ---- weights ------------------------------------------------------------------------------
+ * nn.Conv2d.weight is fp32 OIHW (state_dict contract).  Packed copies are caches.
+ * mode DGRAD packs the 180-degree-rotated, channel-swapped filter so that the input gradient of
+ * a conv is computed by the forward kernel (autograd's convolution_backward for common.py:7-30).
+ * shuffle = r permutes output channels from (c', i, j) to (i, j, c') order (see srb_conv_desc). */
+size_t srb_packed_weight_bytes(int Cout, int Cin, int ksize, int packing, int mode);
+int  srb_pack_weight(srb_ctx*, const float* w_oihw, int Cout, int Cin, int ksize, int packing, int mode,
+                     int shuffle, void* out, void* stream);
+/* bias permuted the same way as the packed output channels (fp32 [Cout]) */
+int  srb_pack_bias(srb_ctx*, const float* bias, int Cout, int shuffle, float* out, void* stream);
+
+/* ---- convolution --------------------------------------------------------------------------
+ * Replaces nn.Conv2d.forward at every call site of models/common.py:7-30 (DefaultConv2d),
+ * rcan.py:41-42,68,101, rdn.py:15,37,59,71-72,87-93, edsr.py:21-33, with the elementwise ops that
+ * follow it in the reference fused into the epilogue.  Also computes autograd's input gradient
+ * when given DGRAD-packed weights (bias = NULL). */
+int  srb_conv(srb_ctx*, const srb_conv_desc*, const void* x, const void* w_packed, const float* bias,
+              const void* residual, const void* mask, void* y, void* y2, float* colsum, void* stream);
+
+/* autograd's weight / bias gradient of the same conv: dw is fp32 OIHW [Cout][Cin][k][k],
+ * dbias fp32 [Cout] (may be NULL). */
+int  srb_conv_wgrad(srb_ctx*, const srb_wgrad_desc*, const void* x, const void* gy,
+                    float* dw_oihw, float* dbias, void* stream);
+/* which kernel family (and hence which weight packing) backend AUTO resolves to */
+int  srb_conv_uses_umma(const srb_conv_desc*);
+int  srb_wgrad_uses_umma(const srb_wgrad_desc*);
+
+/* ---- RCAN channel attention (models/rcan.py:10-29 CALayer + rcan.py:54 `res += x`) ---------
+ * out = t * sigmoid(W2 relu(W1 mean_hw(t) + b1) + b2) + skip.
+ * pooled_sum: [N][C] fp32 sums of t over H*W: an input (from srb_conv's COLSUM) when
+ * compute_pool == 0, filled here first when compute_pool != 0.
+ * s_out [N][C] (mean) and y_out [N][C] (gate) are saved for backward. skip may be NULL. */
+int  srb_ca_fwd(srb_ctx*, int N, int H, int W, int C, int Cr, int dtype,
+                const void* t, const void* skip, float* pooled_sum, int compute_pool,
+                const float* w1, const float* b1, const float* w2, const float* b2,
+                void* out, float* s_out, float* y_out, void* stream);
+/* backward: g = dL/dout.  dt = g*y + broadcast(ds)/HW; parameter grads are accumulated (+=)
+ * when accumulate != 0, else overwritten.  colsum_dt (nullable): per-channel sums of dt over
+ * N,H,W = bias gradient of the conv that produced t.  scratch: [N][C] fp32. */
+int  srb_ca_bwd(srb_ctx*, int N, int H, int W, int C, int Cr, int dtype,
+                const void* g, const void* t, const float* s, const float* y,
+                const float* w1, const float* b1, const float* w2, const float* b2,
+                void* dt, float* dw1, float* db1, float* dw2, float* db2,
+                float* colsum_dt, float* scratch, int accumulate, void* stream);
+
+/* ---- boundary layout conversion (model input / output only) --------------------------------
+ * NCHW fp32 (what SRModel.forward receives, srmodel.py:163) <-> NHWC dtype, with MeanShift
+ * (common.py:58-71, W = I) folded in as a per-channel add (chan_add may be NULL). */
+int  srb_nchw_to_nhwc(srb_ctx*, const float* x, int N, int C, int H, int W, const float* chan_add,
+                      int dtype, void* y, int y_cs, int y_co, void* stream);
+int  srb_nhwc_to_nchw(srb_ctx*, const void* x, int x_cs, int x_co, int dtype, int N, int C, int H, int W,
+                      const float* chan_add, float* y, void* stream);
+
+/* ---- small NHWC helpers --------------------------------------------------------------------*/
+/* dst[.., d_co:d_co+C] = src[.., s_co:s_co+C]  (npix pixels) */
+int  srb_copy_channels(srb_ctx*, const void* src, int s_cs, int s_co, void* dst, int d_cs, int d_co,
+                       int C, int64_t npix, int dtype, void* stream);
+/* out = a + b over channel slices (gradient accumulation at skip connections) */
+int  srb_add_channels(srb_ctx*, const void* a, int a_cs, int a_co, const void* b, int b_cs, int b_co,
+                      void* out, int o_cs, int o_co, int C, int64_t npix, int dtype, void* stream);
+/* ReLU backward over channel slices: out = act > 0 ? g : 0 (autograd of nn.ReLU, common.py:46) */
+int  srb_relu_bwd(srb_ctx*, const void* g, int g_cs, int g_co, const void* act, int a_cs, int a_co,
+                  void* out, int o_cs, int o_co, int C, int64_t npix, int dtype, void* stream);
+/* adjoint of nn.PixelShuffle(r): g [N,H*r,W*r,C'] -> out [N,H,W,r*r*C'] in (i,j,c') channel order */
+int  srb_pixel_unshuffle(srb_ctx*, const void* g, int g_cs, int g_co, void* out, int o_cs, int o_co,
+                         int N, int H, int W, int Cp, int r, int dtype, void* stream);
+/* per-channel sums over npix pixels: out[C] (+= if accumulate) */
+int  srb_colsum(srb_ctx*, const void* x, int x_cs, int x_co, int C, int64_t npix, int dtype,
+                float* out, int accumulate, void* stream);
+
+/* ---- loss (models/srmodel.py:37,549 nn.L1Loss; its autograd seed gradient) ------------------
+ * loss[0] = mean|sr-hr| ; grad = sign(sr-hr)/n  (both NCHW fp32, n elements). grad may be NULL. */
+int  srb_l1_loss(srb_ctx*, const float* sr, const float* hr, int64_t n, float* loss, float* grad,
+                 void* stream);
+
+/* ---- optimizer (models/srmodel.py:57,145-154 optim.Adam over a flat fp32 buffer) ----------- */
+/* step: 1-based step count; if step_dev != NULL the count is read from device memory instead
+ * (so a captured CUDA graph can be replayed; bump it with srb_inc_counter in the same graph).
+ * grad_scale multiplies the gradient first (1/world_size for a summed all-reduce). */
+int  srb_adam_step(srb_ctx*, float* param, const float* grad, float* m, float* v, int64_t n,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                   const int32_t* step_dev, float grad_scale, void* stream);
+int  srb_inc_counter(srb_ctx*, int32_t* counter, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRB200_H */

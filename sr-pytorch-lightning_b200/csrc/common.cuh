@@ -1,0 +1,85 @@
+// Shared helpers for libsrb200 (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/srb200.h"
+
+struct srb_ctx {
+  int device;
+  int num_sms;
+  int smem_optin;
+  void* encode_tiled;  // PFN_cuTensorMapEncodeTiled, resolved at srb_create
+};
+
+void srb_set_error(const char* fmt, ...);
+
+#define SRB_CHECK_CUDA(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      srb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return 1;                                                                           \
+    }                                                                                     \
+  } while (0)
+
+#define SRB_REQUIRE(cond, ...)    \
+  do {                            \
+    if (!(cond)) {                \
+      srb_set_error(__VA_ARGS__); \
+      return 2;                   \
+    }                             \
+  } while (0)
+
+#define SRB_LAUNCH_CHECK() SRB_CHECK_CUDA(cudaGetLastError())
+
+static inline int srb_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- element access -------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float ld_elem(const T* p);
+template <> __device__ __forceinline__ float ld_elem<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ld_elem<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+template <typename T> __device__ __forceinline__ void st_elem(T* p, float v);
+template <> __device__ __forceinline__ void st_elem<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void st_elem<__nv_bfloat16>(__nv_bfloat16* p, float v) {
+  *p = __float2bfloat16_rn(v);
+}
+
+// 4 consecutive channels (16-B for fp32, 8-B for bf16); pointer must be aligned accordingly
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&a);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(a);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}

@@ -1,0 +1,423 @@
+// Bandwidth-bound helpers: weight packing, boundary layout conversion, channel-slice copies/adds,
+// pixel-unshuffle, column sums, L1 loss (+ seed gradient) and Adam.  All HBM/L2-bound: coalesced,
+// vectorised where alignment allows, grid sized from the element count.
+#include "common.cuh"
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---------------------------------------------------------------------------------------------
+// weight packing
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int perm_channel(int co, int Cout, int r) {
+  // nn.PixelShuffle(r) reads conv channel co = c'*r*r + ij; we store channels in (ij, c') order
+  if (r <= 1) return co;
+  int rr = r * r, Cp = Cout / rr;
+  return (co % rr) * Cp + co / rr;
+}
+
+__global__ void pack_simt_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int mode, int shuffle,
+                                 float* __restrict__ out) {
+  int64_t total = (int64_t)Cout * Cin * k * k;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // i indexes the source OIHW
+    int kw = i % k;
+    int kh = (i / k) % k;
+    int ci = (i / (k * k)) % Cin;
+    int co = i / ((int64_t)k * k * Cin);
+    int cop = perm_channel(co, Cout, shuffle);
+    float v = w[i];
+    if (mode == SRB_PACK_FWD) {
+      out[(((int64_t)kh * k + kw) * Cin + ci) * Cout + cop] = v;
+    } else {
+      // dgrad conv: input channels = (permuted) co, output channels = ci, taps rotated by 180 degrees
+      out[(((int64_t)(k - 1 - kh) * k + (k - 1 - kw)) * Cout + cop) * Cin + ci] = v;
+    }
+  }
+}
+
+__global__ void pack_umma_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int mode, int shuffle,
+                                 __nv_bfloat16* __restrict__ out, int cin_e, int cout_e) {
+  // out[chunk][kw][kh][row(cout_e)][64]; effective conv has cin_e inputs, cout_e outputs
+  int nchunk = (cin_e + 63) / 64;
+  int64_t total = (int64_t)nchunk * k * k * cout_e * 64;
+  int rr = shuffle > 1 ? shuffle * shuffle : 1;
+  int Cp = Cout / rr;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int kk = i % 64;
+    int row = (i / 64) % cout_e;
+    int kh = (i / ((int64_t)64 * cout_e)) % k;
+    int kw = (i / ((int64_t)64 * cout_e * k)) % k;
+    int chunk = i / ((int64_t)64 * cout_e * k * k);
+    int cin_idx = chunk * 64 + kk;
+    float v = 0.f;
+    if (cin_idx < cin_e) {
+      if (mode == SRB_PACK_FWD) {
+        // row = permuted output channel -> original co
+        int co = row;
+        if (rr > 1) co = (row % Cp) * rr + row / Cp;
+        v = w[(((int64_t)co * Cin + cin_idx) * k + kh) * k + kw];
+      } else {
+        // effective input channel cin_idx = permuted co; effective output row = ci
+        int co = cin_idx;
+        if (rr > 1) co = (cin_idx % Cp) * rr + cin_idx / Cp;
+        v = w[(((int64_t)co * Cin + row) * k + (k - 1 - kh)) * k + (k - 1 - kw)];
+      }
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+extern "C" size_t srb_packed_weight_bytes(int Cout, int Cin, int ksize, int packing, int mode) {
+  int cin_e = mode == SRB_PACK_FWD ? Cin : Cout;
+  int cout_e = mode == SRB_PACK_FWD ? Cout : Cin;
+  if (packing == SRB_PACK_SIMT) return (size_t)Cout * Cin * ksize * ksize * sizeof(float);
+  return (size_t)((cin_e + 63) / 64) * ksize * ksize * cout_e * 64 * sizeof(__nv_bfloat16);
+}
+
+extern "C" int srb_pack_weight(srb_ctx* ctx, const float* w, int Cout, int Cin, int k, int packing, int mode,
+                               int shuffle, void* out, void* stream) {
+  SRB_REQUIRE(ctx && w && out, "srb_pack_weight: null argument");
+  SRB_REQUIRE(shuffle == 0 || (Cout % (shuffle * shuffle)) == 0, "srb_pack_weight: Cout %d not divisible by r^2", Cout);
+  int64_t total = (int64_t)Cout * Cin * k * k;
+  if (packing == SRB_PACK_SIMT) {
+    int blocks = srb_cdiv(total, 256);
+    if (blocks > 4096) blocks = 4096;
+    pack_simt_kernel<<<blocks, 256, 0, S(stream)>>>(w, Cout, Cin, k, mode, shuffle, (float*)out);
+  } else {
+    int cin_e = mode == SRB_PACK_FWD ? Cin : Cout;
+    int cout_e = mode == SRB_PACK_FWD ? Cout : Cin;
+    int64_t tot2 = (int64_t)((cin_e + 63) / 64) * k * k * cout_e * 64;
+    int blocks = srb_cdiv(tot2, 256);
+    if (blocks > 4096) blocks = 4096;
+    pack_umma_kernel<<<blocks, 256, 0, S(stream)>>>(w, Cout, Cin, k, mode, shuffle, (__nv_bfloat16*)out, cin_e, cout_e);
+  }
+  SRB_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void pack_bias_kernel(const float* __restrict__ b, int Cout, int shuffle, float* __restrict__ out) {
+  int co = blockIdx.x * blockDim.x + threadIdx.x;
+  if (co < Cout) out[perm_channel(co, Cout, shuffle)] = b[co];
+}
+
+extern "C" int srb_pack_bias(srb_ctx* ctx, const float* bias, int Cout, int shuffle, float* out, void* stream) {
+  SRB_REQUIRE(ctx && bias && out, "srb_pack_bias: null argument");
+  pack_bias_kernel<<<srb_cdiv(Cout, 128), 128, 0, S(stream)>>>(bias, Cout, shuffle, out);
+  SRB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// boundary layout conversion
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int N, int C, int H, int W,
+                                    const float* __restrict__ add, T* __restrict__ y, int cs, int co) {
+  int64_t npix = (int64_t)N * H * W;
+  int64_t hw = (int64_t)H * W;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
+    int64_t n = p / hw, r = p % hw;
+    for (int c = 0; c < C; ++c) {
+      float v = x[(n * C + c) * hw + r];
+      if (add) v += add[c];
+      st_elem(y + p * cs + co + c, v);
+    }
+  }
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, int cs, int co, int N, int C, int H, int W,
+                                    const float* __restrict__ add, float* __restrict__ y) {
+  int64_t npix = (int64_t)N * H * W;
+  int64_t hw = (int64_t)H * W;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
+    int64_t n = p / hw, r = p % hw;
+    for (int c = 0; c < C; ++c) {
+      float v = ld_elem(x + p * cs + co + c);
+      if (add) v += add[c];
+      y[(n * C + c) * hw + r] = v;
+    }
+  }
+}
+
+extern "C" int srb_nchw_to_nhwc(srb_ctx* ctx, const float* x, int N, int C, int H, int W, const float* add, int dtype,
+                                void* y, int cs, int co, void* stream) {
+  SRB_REQUIRE(ctx && x && y, "srb_nchw_to_nhwc: null argument");
+  int64_t npix = (int64_t)N * H * W;
+  int blocks = srb_cdiv(npix, 256);
+  if (dtype == SRB_F32)
+    nchw_to_nhwc_kernel<float><<<blocks, 256, 0, S(stream)>>>(x, N, C, H, W, add, (float*)y, cs, co);
+  else
+    nchw_to_nhwc_kernel<__nv_bfloat16><<<blocks, 256, 0, S(stream)>>>(x, N, C, H, W, add, (__nv_bfloat16*)y, cs, co);
+  SRB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srb_nhwc_to_nchw(srb_ctx* ctx, const void* x, int cs, int co, int dtype, int N, int C, int H, int W,
+                                const float* add, float* y, void* stream) {
+  SRB_REQUIRE(ctx && x && y, "srb_nhwc_to_nchw: null argument");
+  int64_t npix = (int64_t)N * H * W;
+  int blocks = srb_cdiv(npix, 256);
+  if (dtype == SRB_F32)
+    nhwc_to_nchw_kernel<float><<<blocks, 256, 0, S(stream)>>>((const float*)x, cs, co, N, C, H, W, add, y);
+  else
+    nhwc_to_nchw_kernel<__nv_bfloat16><<<blocks, 256, 0, S(stream)>>>((const __nv_bfloat16*)x, cs, co, N, C, H, W, add, y);
+  SRB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// channel-slice copy / add, pixel-unshuffle  (4 channels per thread; requires C,cs,co % 4 == 0,
+// scalar fallback otherwise)
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool ADD>
+__global__ void slice_kernel(const T* __restrict__ a, int a_cs, int a_co, const T* __restrict__ b, int b_cs, int b_co,
+                             T* __restrict__ out, int o_cs, int o_co, int C4, int64_t npix) {
+  int64_t total = npix * C4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = i / C4;
+    int c = (int)(i % C4) * 4;
+    float4 v = ld4(a + p * a_cs + a_co + c);
+    if (ADD) {
+      float4 u = ld4(b + p * b_cs + b_co + c);
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    st4(out + p * o_cs + o_co + c, v);
+  }
+}
+
+template <typename T, bool ADD>
+__global__ void slice_scalar_kernel(const T* __restrict__ a, int a_cs, int a_co, const T* __restrict__ b, int b_cs,
+                                    int b_co, T* __restrict__ out, int o_cs, int o_co, int C, int64_t npix) {
+  int64_t total = npix * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = i / C;
+    int c = (int)(i % C);
+    float v = ld_elem(a + p * a_cs + a_co + c);
+    if (ADD) v += ld_elem(b + p * b_cs + b_co + c);
+    st_elem(out + p * o_cs + o_co + c, v);
+  }
+}
+
+template <typename T, bool ADD>
+static int launch_slice(const void* a, int a_cs, int a_co, const void* b, int b_cs, int b_co, void* out, int o_cs,
+                        int o_co, int C, int64_t npix, cudaStream_t st) {
+  bool vec = (C % 4 == 0) && (a_cs % 4 == 0) && (a_co % 4 == 0) && (o_cs % 4 == 0) && (o_co % 4 == 0) &&
+             (!ADD || ((b_cs % 4 == 0) && (b_co % 4 == 0)));
+  if (vec) {
+    int64_t total = npix * (C / 4);
+    int blocks = srb_cdiv(total, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    slice_kernel<T, ADD><<<blocks, 256, 0, st>>>((const T*)a, a_cs, a_co, (const T*)b, b_cs, b_co, (T*)out, o_cs, o_co,
+                                                  C / 4, npix);
+  } else {
+    int64_t total = npix * C;
+    int blocks = srb_cdiv(total, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    slice_scalar_kernel<T, ADD><<<blocks, 256, 0, st>>>((const T*)a, a_cs, a_co, (const T*)b, b_cs, b_co, (T*)out, o_cs,
+                                                         o_co, C, npix);
+  }
+  SRB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srb_copy_channels(srb_ctx* ctx, const void* src, int s_cs, int s_co, void* dst, int d_cs, int d_co, int C,
+                                 int64_t npix, int dtype, void* stream) {
+  SRB_REQUIRE(ctx && src && dst, "srb_copy_channels: null argument");
+  if (dtype == SRB_F32)
+    return launch_slice<float, false>(src, s_cs, s_co, nullptr, 0, 0, dst, d_cs, d_co, C, npix, S(stream));
+  return launch_slice<__nv_bfloat16, false>(src, s_cs, s_co, nullptr, 0, 0, dst, d_cs, d_co, C, npix, S(stream));
+}
+
+extern "C" int srb_add_channels(srb_ctx* ctx, const void* a, int a_cs, int a_co, const void* b, int b_cs, int b_co,
+                                void* out, int o_cs, int o_co, int C, int64_t npix, int dtype, void* stream) {
+  SRB_REQUIRE(ctx && a && b && out, "srb_add_channels: null argument");
+  if (dtype == SRB_F32)
+    return launch_slice<float, true>(a, a_cs, a_co, b, b_cs, b_co, out, o_cs, o_co, C, npix, S(stream));
+  return launch_slice<__nv_bfloat16, true>(a, a_cs, a_co, b, b_cs, b_co, out, o_cs, o_co, C, npix, S(stream));
+}
+
+template <typename T>
+__global__ void unshuffle_kernel(const T* __restrict__ g, int g_cs, int g_co, T* __restrict__ out, int o_cs, int o_co,
+                                 int N, int H, int W, int Cp, int r) {
+  // out[n,h,w, ij*Cp + c] = g[n, h*r+i, w*r+j, c]
+  int rr = r * r;
+  int64_t total = (int64_t)N * H * W * rr * Cp;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int c = idx % Cp;
+    int ij = (idx / Cp) % rr;
+    int64_t p = idx / ((int64_t)Cp * rr);
+    int w = p % W;
+    int h = (p / W) % H;
+    int64_t n = p / ((int64_t)W * H);
+    int i = ij / r, j = ij % r;
+    int64_t gp = (n * (H * r) + (h * r + i)) * (int64_t)(W * r) + (w * r + j);
+    out[p * o_cs + o_co + ij * Cp + c] = g[gp * g_cs + g_co + c];
+  }
+}
+
+extern "C" int srb_pixel_unshuffle(srb_ctx* ctx, const void* g, int g_cs, int g_co, void* out, int o_cs, int o_co, int N,
+                                   int H, int W, int Cp, int r, int dtype, void* stream) {
+  SRB_REQUIRE(ctx && g && out, "srb_pixel_unshuffle: null argument");
+  int64_t total = (int64_t)N * H * W * r * r * Cp;
+  int blocks = srb_cdiv(total, 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (dtype == SRB_F32)
+    unshuffle_kernel<float><<<blocks, 256, 0, S(stream)>>>((const float*)g, g_cs, g_co, (float*)out, o_cs, o_co, N, H, W, Cp, r);
+  else
+    unshuffle_kernel<__nv_bfloat16><<<blocks, 256, 0, S(stream)>>>((const __nv_bfloat16*)g, g_cs, g_co,
+                                                                    (__nv_bfloat16*)out, o_cs, o_co, N, H, W, Cp, r);
+  SRB_LAUNCH_CHECK();
+  return 0;
+}
+
+// out = (act > 0) ? g : 0 over channel slices (ReLU backward, reference: autograd of nn.ReLU)
+template <typename T>
+__global__ void relu_bwd_kernel(const T* __restrict__ g, int g_cs, int g_co, const T* __restrict__ act, int a_cs,
+                                int a_co, T* __restrict__ out, int o_cs, int o_co, int C, int64_t npix) {
+  int64_t total = npix * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = i / C;
+    int c = (int)(i % C);
+    float a = ld_elem(act + p * a_cs + a_co + c);
+    float v = ld_elem(g + p * g_cs + g_co + c);
+    st_elem(out + p * o_cs + o_co + c, a > 0.f ? v : 0.f);
+  }
+}
+
+extern "C" int srb_relu_bwd(srb_ctx* ctx, const void* g, int g_cs, int g_co, const void* act, int a_cs, int a_co,
+                            void* out, int o_cs, int o_co, int C, int64_t npix, int dtype, void* stream) {
+  SRB_REQUIRE(ctx && g && act && out, "srb_relu_bwd: null argument");
+  int64_t total = npix * C;
+  int blocks = srb_cdiv(total, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (dtype == SRB_F32)
+    relu_bwd_kernel<float><<<blocks, 256, 0, S(stream)>>>((const float*)g, g_cs, g_co, (const float*)act, a_cs, a_co,
+                                                          (float*)out, o_cs, o_co, C, npix);
+  else
+    relu_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, S(stream)>>>((const __nv_bfloat16*)g, g_cs, g_co,
+                                                                  (const __nv_bfloat16*)act, a_cs, a_co,
+                                                                  (__nv_bfloat16*)out, o_cs, o_co, C, npix);
+  SRB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-channel sums
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, int cs, int co, int C, int64_t npix, float* __restrict__ out) {
+  // blockDim = (32 channels, 8 pixel lanes); grid.x over channel groups of 32, grid.y over pixel slabs
+  __shared__ float red[8][33];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < C) {
+    for (int64_t p = blockIdx.y * (int64_t)blockDim.y + threadIdx.y; p < npix; p += (int64_t)gridDim.y * blockDim.y)
+      acc += ld_elem(x + p * cs + co + c);
+  }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+    atomicAdd(out + c, s);
+  }
+}
+
+extern "C" int srb_colsum(srb_ctx* ctx, const void* x, int cs, int co, int C, int64_t npix, int dtype, float* out,
+                          int accumulate, void* stream) {
+  SRB_REQUIRE(ctx && x && out, "srb_colsum: null argument");
+  if (!accumulate) SRB_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, S(stream)));
+  dim3 block(32, 8);
+  int slabs = srb_cdiv(npix, 8 * 64);
+  if (slabs > 512) slabs = 512;
+  if (slabs < 1) slabs = 1;
+  dim3 grid(srb_cdiv(C, 32), slabs);
+  if (dtype == SRB_F32)
+    colsum_kernel<float><<<grid, block, 0, S(stream)>>>((const float*)x, cs, co, C, npix, out);
+  else
+    colsum_kernel<__nv_bfloat16><<<grid, block, 0, S(stream)>>>((const __nv_bfloat16*)x, cs, co, C, npix, out);
+  SRB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// L1 loss + seed gradient
+// ---------------------------------------------------------------------------------------------
+__global__ void l1_kernel(const float* __restrict__ sr, const float* __restrict__ hr, int64_t n, float inv_n,
+                          float* __restrict__ loss, float* __restrict__ grad) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float d = sr[i] - hr[i];
+    acc += fabsf(d);
+    if (grad) grad[i] = d > 0.f ? inv_n : (d < 0.f ? -inv_n : 0.f);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(loss, v * inv_n);
+  }
+}
+
+extern "C" int srb_l1_loss(srb_ctx* ctx, const float* sr, const float* hr, int64_t n, float* loss, float* grad,
+                           void* stream) {
+  SRB_REQUIRE(ctx && sr && hr && loss, "srb_l1_loss: null argument");
+  SRB_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), S(stream)));
+  int blocks = srb_cdiv(n, 256 * 8);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  l1_kernel<<<blocks, 256, 0, S(stream)>>>(sr, hr, n, 1.0f / (float)n, loss, grad);
+  SRB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam semantics, amsgrad=False, maximize=False)
+// ---------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float wd,
+                            int step_host, const int32_t* __restrict__ step_dev, float gscale) {
+  int step = step_dev ? *step_dev : step_host;
+  float bc1 = 1.f - powf(b1, (float)step);
+  float bc2 = 1.f - powf(b2, (float)step);
+  float step_size = lr / bc1;
+  float inv_sqrt_bc2 = rsqrtf(bc2);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * gscale;
+    float pi = p[i];
+    if (wd != 0.f) gi += wd * pi;
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    p[i] = pi - step_size * (mi / denom);
+  }
+}
+
+__global__ void inc_kernel(int32_t* c) { *c += 1; }
+
+extern "C" int srb_inc_counter(srb_ctx* ctx, int32_t* counter, void* stream) {
+  SRB_REQUIRE(ctx && counter, "srb_inc_counter: null argument");
+  inc_kernel<<<1, 1, 0, S(stream)>>>(counter);
+  SRB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srb_adam_step(srb_ctx* ctx, float* param, const float* grad, float* m, float* v, int64_t n, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, int step,
+                             const int32_t* step_dev, float grad_scale, void* stream) {
+  SRB_REQUIRE(ctx && param && grad && m && v, "srb_adam_step: null argument");
+  int blocks = srb_cdiv(n, 256 * 4);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  adam_kernel<<<blocks, 256, 0, S(stream)>>>(param, grad, m, v, n, lr, beta1, beta2, eps, weight_decay, step, step_dev,
+                                             grad_scale);
+  SRB_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,43 @@
+"""EDSR on the B200 path (mirror of /root/reference/models/edsr.py:9-54)."""
+from __future__ import annotations
+
+from typing import Any
+
+import torch.nn as nn
+
+from srb200 import functional as F200
+
+from .common import DefaultConv2d, MeanShift, ResBlock, UpscaleBlock
+from .srmodel import SRModel
+
+
+class EDSR(SRModel):
+    """sub_mean -> head 3->F -> n x ResBlock + conv, global skip -> UpscaleBlock -> conv F->3 -> add_mean.
+
+    state_dict keys as the reference: sub_mean.*, add_mean.*, head.0.*, body.{i}.body.{0,2}.*,
+    body.{n}.*, tail.0.{0,2}.*, tail.1.*."""
+
+    def __init__(self, n_feats: int = 64, n_resblocks: int = 16, res_scale: float = 1, **kwargs: dict[str, Any]):
+        super().__init__(**kwargs)
+        k = 3
+        if self._channels == 3:
+            self.sub_mean = MeanShift()
+            self.add_mean = MeanShift(sign=1)
+        self.head = nn.Sequential(DefaultConv2d(self._channels, n_feats, k))
+        body = [ResBlock(n_feats=n_feats, kernel_size=k, res_scale=res_scale) for _ in range(n_resblocks)]
+        body.append(DefaultConv2d(n_feats, n_feats, k))
+        self.body = nn.Sequential(*body)
+        self.tail = nn.Sequential(UpscaleBlock(self._scale_factor, n_feats), DefaultConv2d(n_feats, self._channels, k))
+
+    def forward(self, x):
+        rgb = self._channels == 3
+        x = F200.ToNHWC.apply(x, self.sub_mean.channel_add() if rgb else None, self.act_dtype)
+        x = self.head[0](x)
+        res = x
+        blocks = list(self.body)
+        for blk in blocks[:-1]:
+            res = blk(res)
+        res = blocks[-1](res, residual=x)           # body tail conv + global skip (edsr.py:46-47)
+        y = self.tail[0](res)
+        y = self.tail[1](y)
+        return F200.ToNCHW.apply(y, self.add_mean.channel_add() if rgb else None)

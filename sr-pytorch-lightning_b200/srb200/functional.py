@@ -1,0 +1,320 @@
+"""Differentiable operators of the SR hot path: `torch.autograd.Function`s whose forward AND
+backward are libsrb200 kernel launches (the reference has no custom Functions — its backward is
+autograd over ATen ops; here every adjoint is hand-written).
+
+Gradient delivery for parameters.  By default a Function returns parameter gradients to autograd
+(drop-in with any torch optimizer; with `zero_grad(set_to_none=True)` AccumulateGrad adopts the
+tensor without a copy).  When a parameter carries a `_srb_grad` attribute (a view into a flat
+fp32 gradient buffer installed by `srb200.trainer.FlatParams`), the kernels write straight into
+that view and `None` is returned — one contiguous buffer for the NCCL all-reduce and the fused
+Adam, no per-parameter launches.
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+
+from . import lib as L
+from . import ops
+from .ops import PackedWeights
+
+
+def _grad_target(p: torch.Tensor):
+    """(buffer to write the gradient into, accumulate?, value to return to autograd)."""
+    flat = getattr(p, "_srb_grad", None)
+    if flat is not None:
+        acc = bool(getattr(p, "_srb_grad_live", False))
+        p._srb_grad_live = True
+        return flat, acc, None
+    buf = torch.empty_like(p, memory_format=torch.contiguous_format)
+    return buf, False, buf
+
+
+class ToNHWC(Function):
+    """NCHW fp32 -> NHWC compute dtype, with MeanShift (common.py:58-71) as a per-channel add."""
+
+    @staticmethod
+    def forward(ctx, x, chan_add, dtype):
+        ctx.c = x.shape[1]
+        return ops.nchw_to_nhwc(x.contiguous().float(), chan_add, dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.nhwc_to_nchw(g.contiguous(), 0, ctx.c, None), None, None
+
+
+class ToNCHW(Function):
+    """NHWC compute dtype -> NCHW fp32, with add_mean (edsr.py:52, rcan.py:127) as a per-channel add."""
+
+    @staticmethod
+    def forward(ctx, y, chan_add):
+        ctx.dtype = y.dtype
+        return ops.nhwc_to_nchw(y.contiguous(), 0, y.shape[3], chan_add)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.nchw_to_nhwc(g.contiguous().float(), None, ctx.dtype), None
+
+
+class ConvFn(Function):
+    """y = [PixelShuffle_r]( relu?(conv_k(x) + b) * scale ) + residual?
+
+    Covers DefaultConv2d / nn.Conv2d call sites (common.py:7-30; edsr.py:21-33; rcan.py:68,101;
+    rdn.py:57-59,71-72,87-93) together with the elementwise ops that follow them."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, packs: PackedWeights, relu: bool, scale: float, shuffle: int):
+        assert not (relu and (residual is not None or scale != 1.0)), "unsupported epilogue combination"
+        x = x.contiguous()
+        n, h, w, cin = x.shape
+        cout, _, k, _ = weight.shape
+        r = shuffle if shuffle > 1 else 1
+        y = torch.empty((n, h * r, w * r, cout // (r * r)), dtype=x.dtype, device=x.device)
+        b = packs.get_bias(bias, shuffle) if bias is not None else None
+        res = (residual.contiguous(), 0) if residual is not None else None
+        ops.conv(x, 0, cin, packs, weight, b, y, 0, cout, k, relu=relu, scale=scale, shuffle=shuffle, res=res)
+        ctx.save_for_backward(x, weight, bias, y if relu else None)
+        ctx.packs, ctx.relu, ctx.scale, ctx.shuffle = packs, relu, scale, shuffle
+        ctx.has_res = residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, bias, y = ctx.saved_tensors
+        packs, relu, scale, shuffle = ctx.packs, ctx.relu, ctx.scale, ctx.shuffle
+        g = g.contiguous()
+        cout, cin, k, _ = weight.shape
+        gm = g
+        if relu:
+            gm = torch.empty_like(g)
+            ops.relu_bwd(g, 0, y, 0, gm, 0, g.shape[3])
+        if shuffle > 1:
+            gm = ops.pixel_unshuffle(gm, shuffle)   # [N,H,W,Cout] in (ij, c') channel order
+        dw = db = dx = None
+        if ctx.needs_input_grad[1]:
+            wbuf, wacc, dw = _grad_target(weight)
+            if bias is not None and ctx.needs_input_grad[2]:
+                bbuf, bacc, db = _grad_target(bias)
+                assert bacc == wacc
+            else:
+                bbuf = None
+            ops.conv_wgrad(x, 0, cin, gm, 0, cout, k, wbuf, bbuf, accumulate=wacc, shuffle=shuffle, alpha=scale)
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            if shuffle > 1:
+                assert scale == 1.0
+                ops.conv_dgrad_shuffled(gm, packs, weight, dx, shuffle)
+            else:
+                ops.conv(gm, 0, cout, packs, weight, None, dx, 0, cin, k, mode=L.PACK_DGRAD, scale=scale)
+        dres = g if ctx.has_res else None
+        return dx, dw, db, dres, None, None, None, None
+
+
+class ResBlockFn(Function):
+    """EDSR ResBlock (common.py:74-109): out = conv2(relu(conv1(x))) * res_scale + x."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, p1: PackedWeights, p2: PackedWeights, scale: float):
+        x = x.contiguous()
+        c = x.shape[3]
+        y1 = torch.empty_like(x)
+        ops.conv(x, 0, c, p1, w1, b1.detach(), y1, 0, c, 3, relu=True)
+        out = torch.empty_like(x)
+        ops.conv(y1, 0, c, p2, w2, b2.detach(), out, 0, c, 3, scale=scale, res=(x, 0))
+        ctx.save_for_backward(x, y1, w1, b1, w2, b2)
+        ctx.p1, ctx.p2, ctx.scale = p1, p2, scale
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y1, w1, b1, w2, b2 = ctx.saved_tensors
+        g = g.contiguous()
+        c = x.shape[3]
+        w2buf, acc2, dw2 = _grad_target(w2)
+        b2buf, _, db2 = _grad_target(b2)
+        ops.conv_wgrad(y1, 0, c, g, 0, c, 3, w2buf, b2buf, accumulate=acc2, alpha=ctx.scale)
+        d1 = torch.empty_like(x)
+        ops.conv(g, 0, c, ctx.p2, w2, None, d1, 0, c, 3, mode=L.PACK_DGRAD, scale=ctx.scale, mask=(y1, 0))
+        w1buf, acc1, dw1 = _grad_target(w1)
+        b1buf, _, db1 = _grad_target(b1)
+        ops.conv_wgrad(x, 0, c, d1, 0, c, 3, w1buf, b1buf, accumulate=acc1)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            ops.conv(d1, 0, c, ctx.p1, w1, None, dx, 0, c, 3, mode=L.PACK_DGRAD, res=(g, 0))
+        return dx, dw1, db1, dw2, db2, None, None, None
+
+
+class RCABFn(Function):
+    """RCAN residual channel-attention block (rcan.py:33-55):
+    out = CA(conv2(relu(conv1(x)))) + x, CA = rcan.py:10-29.  conv2's epilogue emits the pooled
+    sums, one streaming kernel applies gate + skip."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, cw1, cb1, cw2, cb2, p1: PackedWeights, p2: PackedWeights):
+        x = x.contiguous()
+        n, h, w, c = x.shape
+        y1 = torch.empty_like(x)
+        ops.conv(x, 0, c, p1, w1, b1.detach(), y1, 0, c, 3, relu=True)
+        t = torch.empty_like(x)
+        pool = torch.zeros((n, c), dtype=torch.float32, device=x.device)
+        ops.conv(y1, 0, c, p2, w2, b2.detach(), t, 0, c, 3, colsum=pool, colsum_groups=n)
+        out = torch.empty_like(x)
+        s = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        yg = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        ops.ca_fwd(t, x, pool, False, cw1.detach(), cb1.detach(), cw2.detach(), cb2.detach(), out, s, yg)
+        ctx.save_for_backward(x, y1, t, s, yg, w1, b1, w2, b2, cw1, cb1, cw2, cb2)
+        ctx.p1, ctx.p2 = p1, p2
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y1, t, s, yg, w1, b1, w2, b2, cw1, cb1, cw2, cb2 = ctx.saved_tensors
+        g = g.contiguous()
+        n, h, w, c = x.shape
+        dt = torch.empty_like(t)
+        cw1buf, cacc, dcw1 = _grad_target(cw1)
+        cb1buf, _, dcb1 = _grad_target(cb1)
+        cw2buf, _, dcw2 = _grad_target(cw2)
+        cb2buf, _, dcb2 = _grad_target(cb2)
+        b2buf, bacc2, db2 = _grad_target(b2)
+        scratch = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        if cacc != bacc2:
+            raise RuntimeError("inconsistent gradient-accumulation state between CA and conv parameters")
+        ops.ca_bwd(g, t, s, yg, cw1, cb1, cw2, cb2, dt, cw1buf, cb1buf, cw2buf, cb2buf, b2buf, scratch, accumulate=cacc)
+        w2buf, acc2, dw2 = _grad_target(w2)
+        ops.conv_wgrad(y1, 0, c, dt, 0, c, 3, w2buf, None, accumulate=acc2)
+        d1 = torch.empty_like(x)
+        b1buf, bacc1, db1 = _grad_target(b1)
+        if not bacc1:
+            b1buf.zero_()
+        ops.conv(dt, 0, c, ctx.p2, w2, None, d1, 0, c, 3, mode=L.PACK_DGRAD, mask=(y1, 0), colsum=b1buf, colsum_groups=1)
+        w1buf, acc1, dw1 = _grad_target(w1)
+        ops.conv_wgrad(x, 0, c, d1, 0, c, 3, w1buf, None, accumulate=acc1)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            ops.conv(d1, 0, c, ctx.p1, w1, None, dx, 0, c, 3, mode=L.PACK_DGRAD, res=(g, 0))
+        return dx, dw1, db1, dw2, db2, dcw1, dcb1, dcw2, dcb2, None, None
+
+
+class RDBFn(Function):
+    """RDN residual dense block (rdn.py:24-40).  The C dense layers read a channel prefix of ONE
+    [N,H,W,G0+C*G] buffer and write their G new channels in place (no torch.cat, rdn.py:21);
+    LFF 1x1 + skip (rdn.py:40) closes the block."""
+
+    @staticmethod
+    def forward(ctx, x, packs, g0: int, g: int, *params):
+        # params = (w_0, b_0, ..., w_{C-1}, b_{C-1}, w_lff, b_lff)
+        x = x.contiguous()
+        n, h, w, _ = x.shape
+        nl = (len(params) - 2) // 2
+        ctot = g0 + nl * g
+        dbuf = torch.empty((n, h, w, ctot), dtype=x.dtype, device=x.device)
+        ops.copy_channels(x, 0, dbuf, 0, g0)
+        for c in range(nl):
+            ops.conv(dbuf, 0, g0 + c * g, packs[c], params[2 * c], params[2 * c + 1].detach(), dbuf, g0 + c * g, g, 3,
+                     relu=True)
+        out = torch.empty_like(x)
+        ops.conv(dbuf, 0, ctot, packs[nl], params[-2], params[-1].detach(), out, 0, g0, 1, res=(x, 0))
+        ctx.save_for_backward(dbuf, *params)
+        ctx.packs, ctx.g0, ctx.g, ctx.nl = packs, g0, g, nl
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        dbuf, *params = ctx.saved_tensors
+        packs, g0, g, nl = ctx.packs, ctx.g0, ctx.g, ctx.nl
+        gout = gout.contiguous()
+        ctot = g0 + nl * g
+        grads = [None] * len(params)
+        # LFF (1x1): weight grad, then its input gradient fills the whole dense gradient buffer
+        wbuf, acc, grads[-2] = _grad_target(params[-2])
+        bbuf, _, grads[-1] = _grad_target(params[-1])
+        ops.conv_wgrad(dbuf, 0, ctot, gout, 0, g0, 1, wbuf, bbuf, accumulate=acc)
+        gd = torch.empty_like(dbuf)
+        ops.conv(gout, 0, g0, packs[nl], params[-2], None, gd, 0, ctot, 1, mode=L.PACK_DGRAD)
+        for c in range(nl - 1, -1, -1):
+            off = g0 + c * g
+            ops.relu_bwd(gd, off, dbuf, off, gd, off, g)     # in place on the slice
+            wbuf, acc, grads[2 * c] = _grad_target(params[2 * c])
+            bbuf, _, grads[2 * c + 1] = _grad_target(params[2 * c + 1])
+            ops.conv_wgrad(dbuf, 0, off, gd, off, g, 3, wbuf, bbuf, accumulate=acc)
+            # gd[..., :off] += dgrad(gd[..., off:off+g])   (read-modify-write of the same element)
+            ops.conv(gd, off, g, packs[c], params[2 * c], None, gd, 0, off, 3, mode=L.PACK_DGRAD, res=(gd, 0))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(gout)
+            ops.add_channels(gd, 0, gout, 0, dx, 0, g0)
+        return (dx, None, None, None, *grads)
+
+
+class ConcatConv1x1Fn(Function):
+    """GFF.0 (rdn.py:70-71,108): 1x1 conv over the channel concatenation of all RDB outputs.
+    The concat buffer is filled by channel-slice copies; its gradient is handed back as slices."""
+
+    @staticmethod
+    def forward(ctx, weight, bias, packs: PackedWeights, *xs):
+        n, h, w, c = xs[0].shape
+        ctot = c * len(xs)
+        cat = torch.empty((n, h, w, ctot), dtype=xs[0].dtype, device=xs[0].device)
+        for i, xi in enumerate(xs):
+            ops.copy_channels(xi.contiguous(), 0, cat, i * c, c)
+        cout = weight.shape[0]
+        y = torch.empty((n, h, w, cout), dtype=cat.dtype, device=cat.device)
+        ops.conv(cat, 0, ctot, packs, weight, bias.detach(), y, 0, cout, 1)
+        ctx.save_for_backward(cat, weight, bias)
+        ctx.packs, ctx.c, ctx.k = packs, c, len(xs)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        cat, weight, bias = ctx.saved_tensors
+        g = g.contiguous()
+        cout, ctot = weight.shape[0], weight.shape[1]
+        wbuf, acc, dw = _grad_target(weight)
+        bbuf, _, db = _grad_target(bias)
+        ops.conv_wgrad(cat, 0, ctot, g, 0, cout, 1, wbuf, bbuf, accumulate=acc)
+        gcat = torch.empty_like(cat)
+        ops.conv(g, 0, cout, ctx.packs, weight, None, gcat, 0, ctot, 1, mode=L.PACK_DGRAD)
+        outs = []
+        for i in range(ctx.k):
+            gi = torch.empty(cat.shape[:3] + (ctx.c,), dtype=cat.dtype, device=cat.device)
+            ops.copy_channels(gcat, i * ctx.c, gi, 0, ctx.c)
+            outs.append(gi)
+        return (dw, db, None, *outs)
+
+
+class AddFn(Function):
+    """Skip connection between two NHWC tensors (edsr.py:47, rdn.py:109) as one kernel."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a = a.contiguous()
+        b = b.contiguous()
+        out = torch.empty_like(a)
+        ops.add_channels(a, 0, b, 0, out, 0, a.shape[3])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+class L1LossFn(Function):
+    """nn.L1Loss() (srmodel.py:37,549) with its seed gradient sign(sr-hr)/n computed in the same pass."""
+
+    @staticmethod
+    def forward(ctx, sr, hr):
+        loss, grad = ops.l1_loss(sr.contiguous(), hr.contiguous(), want_grad=True)
+        ctx.save_for_backward(grad)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None
+
+
+def l1_loss(sr, hr):
+    return L1LossFn.apply(sr, hr)

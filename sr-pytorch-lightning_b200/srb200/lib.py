@@ -1,0 +1,111 @@
+"""ctypes binding of libsrb200.so (C ABI: include/srb200.h).
+
+There is NO CPU fallback: if the shared library is missing or a kernel reports an error the
+product path raises (`RuntimeError`, the exception class the reference's training loop catches,
+/root/reference/train.py:237-253).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("SRB200_LIB", os.path.join(os.path.dirname(_HERE), "csrc", "libsrb200.so"))
+
+F32, BF16 = 0, 1
+RELU, RESIDUAL, MASK, COLSUM, OUT2 = 1, 2, 4, 8, 16
+PACK_SIMT, PACK_UMMA = 0, 1
+PACK_FWD, PACK_DGRAD = 0, 1
+BACKEND_AUTO, BACKEND_SIMT, BACKEND_UMMA = 0, 1, 2
+
+c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [(n, c_i32) for n in ("N", "H", "W", "Cin", "Cout", "ksize", "dtype", "flags")] + \
+               [("scale", c_f32)] + \
+               [(n, c_i32) for n in ("shuffle", "colsum_groups", "backend", "x_cs", "x_co", "y_cs", "y_co",
+                                     "r_cs", "r_co", "m_cs", "m_co", "y2_cs", "y2_co")]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [(n, c_i32) for n in ("N", "H", "W", "Cin", "Cout", "ksize", "dtype", "accumulate", "shuffle",
+                                     "backend", "x_cs", "x_co", "g_cs", "g_co")] + [("alpha", c_f32)]
+
+
+# name -> (restype, argtypes); every symbol include/srb200.h declares
+PROTOTYPES = {
+    "srb_abi_version": (c_i32, []),
+    "srb_last_error": (C.c_char_p, []),
+    "srb_create": (c_i32, [c_i32, C.POINTER(c_vp)]),
+    "srb_destroy": (c_i32, [c_vp]),
+    "srb_num_sms": (c_i32, [c_vp]),
+    "srb_packed_weight_bytes": (C.c_size_t, [c_i32, c_i32, c_i32, c_i32, c_i32]),
+    "srb_pack_weight": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "srb_pack_bias": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    "srb_conv": (c_i32, [c_vp, C.POINTER(ConvDesc)] + [c_vp] * 9),
+    "srb_conv_wgrad": (c_i32, [c_vp, C.POINTER(WgradDesc)] + [c_vp] * 5),
+    "srb_conv_uses_umma": (c_i32, [C.POINTER(ConvDesc)]),
+    "srb_wgrad_uses_umma": (c_i32, [C.POINTER(WgradDesc)]),
+    "srb_ca_fwd": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32] + [c_vp] * 8),
+    "srb_ca_bwd": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32] + [c_vp] * 15 + [c_i32, c_vp]),
+    "srb_nchw_to_nhwc": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp]),
+    "srb_nhwc_to_nchw": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "srb_copy_channels": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_i64, c_i32, c_vp]),
+    "srb_add_channels": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_i64, c_i32, c_vp]),
+    "srb_relu_bwd": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_i64, c_i32, c_vp]),
+    "srb_pixel_unshuffle": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "srb_colsum": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i64, c_i32, c_vp, c_i32, c_vp]),
+    "srb_l1_loss": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "srb_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_vp, c_f32, c_vp]),
+    "srb_inc_counter": (c_i32, [c_vp, c_vp, c_vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+_ctx: dict[int, int] = {}
+
+
+def load():
+    """dlopen libsrb200.so and bind every prototype; raises if the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"libsrb200.so not found at {LIB_PATH}: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C sr-pytorch-lightning_b200/csrc`). There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is missing
+            fn.restype = res
+            fn.argtypes = args
+        if lib.srb_abi_version() != 1:
+            raise RuntimeError(f"libsrb200.so ABI version {lib.srb_abi_version()} != 1")
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().srb_last_error().decode(errors="replace")
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        raise RuntimeError(f"libsrb200 {what} failed (code {rc}): {last_error()}")
+
+
+def ctx(device_index: int) -> int:
+    """Per-device context handle (created on first use)."""
+    h = _ctx.get(device_index)
+    if h is None:
+        lib = load()
+        out = c_vp()
+        check(lib.srb_create(int(device_index), C.byref(out)), "srb_create")
+        h = out.value
+        _ctx[device_index] = h
+    return h

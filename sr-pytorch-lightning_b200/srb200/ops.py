@@ -1,0 +1,272 @@
+"""Host-side operator layer: thin, non-differentiable launch wrappers over the C ABI
+(include/srb200.h).  Tensors are torch CUDA tensors used purely as device memory; every launch
+goes to `torch.cuda.current_stream()` so Lightning/AMP/DDP stream ordering and CUDA-graph capture
+work (SURVEY §8b "Threading / streams").
+
+Activations: NHWC contiguous `[N, H, W, Cs]` tensors (bf16 or fp32).  A *channel slice* is
+addressed as (tensor, channel_offset, channels) — the replacement for torch.cat in RDN
+(/root/reference/models/rdn.py:21,108).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import lib as L
+
+_DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _ctx(t):
+    if not t.is_cuda:
+        raise RuntimeError("srb200 kernels need CUDA tensors (there is no CPU fallback)")
+    return C.c_void_p(L.ctx(t.device.index if t.device.index is not None else torch.cuda.current_device()))
+
+
+def _nhwc(t):
+    assert t.dim() == 4 and t.is_contiguous(), "activation must be a contiguous NHWC tensor"
+    return t.shape
+
+
+def dtype_code(t):
+    return _DT[t.dtype]
+
+
+# --------------------------------------------------------------------------------------------
+# weights
+# --------------------------------------------------------------------------------------------
+def pack_weight(w: torch.Tensor, packing: int, mode: int, shuffle: int = 0) -> torch.Tensor:
+    """fp32 OIHW parameter -> packed device buffer (uint8 tensor)."""
+    lib = L.load()
+    assert w.dtype == torch.float32 and w.is_contiguous()
+    cout, cin, k, _ = w.shape
+    nbytes = lib.srb_packed_weight_bytes(cout, cin, k, packing, mode)
+    out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    L.check(lib.srb_pack_weight(_ctx(w), _p(w), cout, cin, k, packing, mode, shuffle, _p(out), _stream()), "srb_pack_weight")
+    return out
+
+
+def pack_bias(b: torch.Tensor, shuffle: int) -> torch.Tensor:
+    if shuffle <= 1:
+        return b
+    lib = L.load()
+    out = torch.empty_like(b)
+    L.check(lib.srb_pack_bias(_ctx(b), _p(b), b.numel(), shuffle, _p(out), _stream()), "srb_pack_bias")
+    return out
+
+
+class PackedWeights:
+    """Cache of packed copies of one conv weight, rebuilt when the parameter changes
+    (keyed on data_ptr and the tensor version counter, SURVEY §8b "Ownership")."""
+
+    def __init__(self):
+        self._cache = {}
+
+    def get(self, w: torch.Tensor, packing: int, mode: int, shuffle: int = 0):
+        key = (packing, mode, shuffle)
+        tag = (w.data_ptr(), w._version, w.device)
+        hit = self._cache.get(key)
+        if hit is not None and hit[0] == tag:
+            return hit[1]
+        packed = pack_weight(w.detach(), packing, mode, shuffle)
+        self._cache[key] = (tag, packed)
+        return packed
+
+    def get_bias(self, b: torch.Tensor, shuffle: int):
+        if b is None or shuffle <= 1:
+            return b.detach() if b is not None else None
+        key = ("bias", shuffle)
+        tag = (b.data_ptr(), b._version, b.device)
+        hit = self._cache.get(key)
+        if hit is not None and hit[0] == tag:
+            return hit[1]
+        packed = pack_bias(b.detach(), shuffle)
+        self._cache[key] = (tag, packed)
+        return packed
+
+
+# --------------------------------------------------------------------------------------------
+# convolution
+# --------------------------------------------------------------------------------------------
+def make_conv_desc(x, x_co, cin, y, y_co, cout, k, *, flags=0, scale=1.0, shuffle=0, res=None, mask=None, y2=None,
+                   colsum_groups=0, backend=L.BACKEND_AUTO) -> L.ConvDesc:
+    n, h, w, xcs = _nhwc(x)
+    d = L.ConvDesc()
+    d.N, d.H, d.W = n, h, w
+    d.Cin, d.Cout, d.ksize = cin, cout, k
+    d.dtype = dtype_code(x)
+    d.flags = flags
+    d.scale = float(scale)
+    d.shuffle = shuffle
+    d.colsum_groups = colsum_groups
+    d.backend = backend
+    d.x_cs, d.x_co = xcs, x_co
+    d.y_cs, d.y_co = y.shape[3], y_co
+    if res is not None:
+        d.r_cs, d.r_co = res[0].shape[3], res[1]
+    if mask is not None:
+        d.m_cs, d.m_co = mask[0].shape[3], mask[1]
+    if y2 is not None:
+        d.y2_cs, d.y2_co = y2[0].shape[3], y2[1]
+    return d
+
+
+def conv_uses_umma(desc: L.ConvDesc) -> bool:
+    return bool(L.load().srb_conv_uses_umma(C.byref(desc)))
+
+
+def conv(x, x_co, cin, weights: PackedWeights, w_param, bias, y, y_co, cout, k, *, mode=L.PACK_FWD, relu=False,
+         scale=1.0, shuffle=0, res=None, mask=None, y2=None, colsum=None, colsum_groups=0, backend=L.BACKEND_AUTO):
+    """y[..., y_co:y_co+cout'] = epilogue(conv(x[..., x_co:x_co+cin])).
+
+    mode PACK_DGRAD: `w_param` is the forward parameter [cin_fwd=cout, ...]; the kernel computes
+    the input gradient (here `cin` = forward Cout, `cout` = forward Cin).
+    res / mask / y2: (tensor, channel_offset) on the output pixel grid."""
+    lib = L.load()
+    flags = (L.RELU if relu else 0) | (L.RESIDUAL if res is not None else 0) | (L.MASK if mask is not None else 0) | \
+            (L.OUT2 if y2 is not None else 0) | (L.COLSUM if colsum is not None else 0)
+    d = make_conv_desc(x, x_co, cin, y, y_co, cout, k, flags=flags, scale=scale, shuffle=shuffle, res=res, mask=mask,
+                       y2=y2, colsum_groups=colsum_groups, backend=backend)
+    packing = L.PACK_UMMA if conv_uses_umma(d) else L.PACK_SIMT
+    if backend == L.BACKEND_UMMA:
+        packing = L.PACK_UMMA
+    # for DGRAD the pixel-shuffle permutation applies to the (forward) output channels = our inputs
+    wp = weights.get(w_param, packing, mode, shuffle if mode == L.PACK_FWD else 0)
+    L.check(lib.srb_conv(_ctx(x), C.byref(d), _p(x), _p(wp), _p(bias), _p(res[0]) if res else None,
+                         _p(mask[0]) if mask else None, _p(y), _p(y2[0]) if y2 else None, _p(colsum), _stream()),
+            "srb_conv")
+    return y
+
+
+def conv_dgrad_shuffled(gu, weights: PackedWeights, w_param, y, shuffle, **kw):
+    """Input gradient of a conv whose output went through PixelShuffle(r): `gu` is the
+    un-shuffled gradient in (ij, c') channel order, so the DGRAD packing must permute its input
+    channels the same way."""
+    lib = L.load()
+    cout_f, cin_f, k, _ = w_param.shape
+    res = kw.get("res")
+    flags = (L.RESIDUAL if res is not None else 0)
+    d = make_conv_desc(gu, 0, cout_f, y, 0, cin_f, k, flags=flags, res=res)
+    packing = L.PACK_UMMA if conv_uses_umma(d) else L.PACK_SIMT
+    wp = weights.get(w_param, packing, L.PACK_DGRAD, shuffle)
+    L.check(lib.srb_conv(_ctx(gu), C.byref(d), _p(gu), _p(wp), None, _p(res[0]) if res else None, None, _p(y), None,
+                         None, _stream()), "srb_conv(dgrad)")
+    return y
+
+
+def conv_wgrad(x, x_co, cin, gy, g_co, cout, k, dw, dbias, *, accumulate=False, shuffle=0, alpha=1.0,
+               backend=L.BACKEND_AUTO):
+    """dw (fp32 OIHW) (+)= alpha * correlation(x, gy); dbias (+)= alpha * sum(gy)."""
+    lib = L.load()
+    n, h, w, xcs = _nhwc(x)
+    d = L.WgradDesc()
+    d.N, d.H, d.W = n, h, w
+    d.Cin, d.Cout, d.ksize = cin, cout, k
+    d.dtype = dtype_code(x)
+    d.accumulate = 1 if accumulate else 0
+    d.shuffle = shuffle
+    d.backend = backend
+    d.x_cs, d.x_co = xcs, x_co
+    d.g_cs, d.g_co = gy.shape[3], g_co
+    d.alpha = float(alpha)
+    L.check(lib.srb_conv_wgrad(_ctx(x), C.byref(d), _p(x), _p(gy), _p(dw), _p(dbias), _stream()), "srb_conv_wgrad")
+
+
+# --------------------------------------------------------------------------------------------
+# channel attention
+# --------------------------------------------------------------------------------------------
+def ca_fwd(t, skip, pooled_sum, compute_pool, w1, b1, w2, b2, out, s_out, y_out):
+    n, h, w, c = _nhwc(t)
+    cr = w1.shape[0]
+    L.check(L.load().srb_ca_fwd(_ctx(t), n, h, w, c, cr, dtype_code(t), _p(t), _p(skip), _p(pooled_sum),
+                                1 if compute_pool else 0, _p(w1), _p(b1), _p(w2), _p(b2), _p(out), _p(s_out), _p(y_out),
+                                _stream()), "srb_ca_fwd")
+
+
+def ca_bwd(g, t, s, y, w1, b1, w2, b2, dt, dw1, db1, dw2, db2, colsum_dt, scratch, accumulate=False):
+    n, h, w, c = _nhwc(t)
+    cr = w1.shape[0]
+    L.check(L.load().srb_ca_bwd(_ctx(t), n, h, w, c, cr, dtype_code(t), _p(g), _p(t), _p(s), _p(y), _p(w1), _p(b1),
+                                _p(w2), _p(b2), _p(dt), _p(dw1), _p(db1), _p(dw2), _p(db2), _p(colsum_dt), _p(scratch),
+                                1 if accumulate else 0, _stream()), "srb_ca_bwd")
+
+
+# --------------------------------------------------------------------------------------------
+# layout / elementwise
+# --------------------------------------------------------------------------------------------
+def nchw_to_nhwc(x, chan_add, dtype, out=None, out_co=0):
+    n, c, h, w = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    if out is None:
+        out = torch.empty((n, h, w, c), dtype=dtype, device=x.device)
+    L.check(L.load().srb_nchw_to_nhwc(_ctx(x), _p(x), n, c, h, w, _p(chan_add), dtype_code(out), _p(out),
+                                      out.shape[3], out_co, _stream()), "srb_nchw_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw(x, x_co, c, chan_add):
+    n, h, w, cs = _nhwc(x)
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    L.check(L.load().srb_nhwc_to_nchw(_ctx(x), _p(x), cs, x_co, dtype_code(x), n, c, h, w, _p(chan_add), _p(out),
+                                      _stream()), "srb_nhwc_to_nchw")
+    return out
+
+
+def copy_channels(src, s_co, dst, d_co, c):
+    npix = src.shape[0] * src.shape[1] * src.shape[2]
+    L.check(L.load().srb_copy_channels(_ctx(src), _p(src), src.shape[3], s_co, _p(dst), dst.shape[3], d_co, c, npix,
+                                       dtype_code(src), _stream()), "srb_copy_channels")
+
+
+def add_channels(a, a_co, b, b_co, out, o_co, c):
+    npix = a.shape[0] * a.shape[1] * a.shape[2]
+    L.check(L.load().srb_add_channels(_ctx(a), _p(a), a.shape[3], a_co, _p(b), b.shape[3], b_co, _p(out), out.shape[3],
+                                      o_co, c, npix, dtype_code(a), _stream()), "srb_add_channels")
+
+
+def relu_bwd(g, g_co, act, a_co, out, o_co, c):
+    npix = g.shape[0] * g.shape[1] * g.shape[2]
+    L.check(L.load().srb_relu_bwd(_ctx(g), _p(g), g.shape[3], g_co, _p(act), act.shape[3], a_co, _p(out), out.shape[3],
+                                  o_co, c, npix, dtype_code(g), _stream()), "srb_relu_bwd")
+
+
+def pixel_unshuffle(g, r):
+    n, hr, wr, cp = _nhwc(g)
+    h, w = hr // r, wr // r
+    out = torch.empty((n, h, w, cp * r * r), dtype=g.dtype, device=g.device)
+    L.check(L.load().srb_pixel_unshuffle(_ctx(g), _p(g), cp, 0, _p(out), cp * r * r, 0, n, h, w, cp, r, dtype_code(g),
+                                         _stream()), "srb_pixel_unshuffle")
+    return out
+
+
+def colsum(x, x_co, c, out, accumulate=False):
+    npix = x.shape[0] * x.shape[1] * x.shape[2]
+    L.check(L.load().srb_colsum(_ctx(x), _p(x), x.shape[3], x_co, c, npix, dtype_code(x), _p(out),
+                                1 if accumulate else 0, _stream()), "srb_colsum")
+
+
+def l1_loss(sr, hr, want_grad=True):
+    """(loss[1] fp32, grad or None): mean |sr - hr| and sign(sr-hr)/n (srmodel.py:37,549)."""
+    assert sr.dtype == torch.float32 and hr.dtype == torch.float32 and sr.is_contiguous() and hr.is_contiguous()
+    loss = torch.empty(1, dtype=torch.float32, device=sr.device)
+    grad = torch.empty_like(sr) if want_grad else None
+    L.check(L.load().srb_l1_loss(_ctx(sr), _p(sr), _p(hr), sr.numel(), _p(loss), _p(grad), _stream()), "srb_l1_loss")
+    return loss, grad
+
+
+def adam_step(param, grad, m, v, *, lr, beta1, beta2, eps, weight_decay, step, step_dev=None, grad_scale=1.0):
+    L.check(L.load().srb_adam_step(_ctx(param), _p(param), _p(grad), _p(m), _p(v), param.numel(), lr, beta1, beta2, eps,
+                                   weight_decay, int(step), _p(step_dev), grad_scale, _stream()), "srb_adam_step")
+
+
+def inc_counter(counter):
+    L.check(L.load().srb_inc_counter(_ctx(counter), _p(counter), _stream()), "srb_inc_counter")

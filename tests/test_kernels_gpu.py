@@ -1,0 +1,359 @@
+"""Kernel-level parity (GPU): every libsrb200 kernel, called through the C ABI (ctypes), against
+the plain-torch fp64 definition of the same op on the same seeded inputs.
+
+Tolerances: fp32 kernels 1e-5 relative (accumulation-order noise only); bf16 kernels compare
+against the fp64 result computed FROM THE SAME bf16-rounded operands, so only the fp32
+accumulation and the final bf16 rounding (2^-8 relative) separate them."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+def _nhwc(t):  # NCHW (cpu, any dtype) -> NHWC contiguous
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+def _rel(a, b):
+    a = a.double().cpu()
+    b = b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item(), ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def _conv_case(dtype, n, h, w, cin, cout, k, *, relu=False, scale=1.0, residual=False, mask=False, shuffle=0,
+               colsum=0, backend=0, seed=0, x_cs=None, x_co=0, y_cs=None, y_co=0):
+    from srb200 import lib as L, ops
+    g = torch.Generator().manual_seed(seed)
+    xs = cin if x_cs is None else x_cs
+    xfull = torch.randn(n, h, w, xs, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    r = shuffle if shuffle > 1 else 1
+    cp = cout // (r * r)
+    ys = cp if y_cs is None else y_cs
+    res_t = torch.randn(n, h * r, w * r, cp, generator=g) if residual else None
+    mask_t = torch.randn(n, h * r, w * r, cp, generator=g) if mask else None
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    # operands as the kernel sees them
+    xq = xfull.to(tdt)
+    wq = wt.to(tdt).float() if (dtype == "bf16" and backend != L.BACKEND_SIMT) else wt
+    resq = res_t.to(tdt) if residual else None
+    maskq = mask_t.to(tdt) if mask else None
+    # ---- fp64 definition
+    xin = _nchw(xq[..., x_co:x_co + cin].double())
+    ref = F.conv2d(xin, wq.double(), bias.double(), padding=k // 2)
+    if relu:
+        ref = ref.relu()
+    ref = ref * scale
+    if r > 1:
+        ref = F.pixel_shuffle(ref, r)
+    if mask:
+        ref = torch.where(_nchw(maskq.double()) > 0, ref, torch.zeros_like(ref))
+    if residual:
+        ref = ref + _nchw(resq.double())
+    ref = _nhwc(ref)
+    # ---- kernel
+    dev = _dev()
+    xd = xq.to(dev)
+    y = torch.full((n, h * r, w * r, ys), 7.0, dtype=tdt, device=dev)
+    packs = ops.PackedWeights()
+    wd = wt.to(dev)
+    bd = packs.get_bias(bias.to(dev), shuffle)
+    cs = None
+    groups = 0
+    if colsum:
+        groups = n if colsum == 2 else 1
+        cs = torch.zeros(groups, cout, dtype=torch.float32, device=dev)
+    ops.conv(xd, x_co, cin, packs, wd, bd, y, y_co, cout, k, relu=relu, scale=scale, shuffle=shuffle,
+             res=(resq.to(dev), 0) if residual else None, mask=(maskq.to(dev), 0) if mask else None,
+             colsum=cs, colsum_groups=groups, backend=backend)
+    torch.cuda.synchronize()
+    out = y[..., y_co:y_co + cp].float().cpu()
+    if ys != cp:  # untouched channels must keep the fill value
+        untouched = torch.cat([y[..., :y_co], y[..., y_co + cp:]], dim=-1).float().cpu()
+        assert torch.all(untouched == 7.0), "kernel wrote outside its channel slice"
+    return out, ref, cs, xd, y
+
+
+SIMT_CASES = [
+    dict(n=2, h=9, w=11, cin=3, cout=64, k=3),
+    dict(n=1, h=16, w=16, cin=64, cout=64, k=3, relu=True),
+    dict(n=2, h=8, w=8, cin=64, cout=3, k=3),
+    dict(n=1, h=12, w=10, cin=64, cout=64, k=3, scale=0.1, residual=True),
+    dict(n=1, h=8, w=8, cin=32, cout=32, k=3, mask=True, residual=True),
+    dict(n=1, h=8, w=8, cin=16, cout=36, k=3, shuffle=3),
+    dict(n=2, h=8, w=8, cin=16, cout=32, k=3, shuffle=2, residual=True),
+    dict(n=1, h=10, w=10, cin=3, cout=64, k=9, relu=True),
+    dict(n=1, h=10, w=10, cin=32, cout=3, k=5),
+    dict(n=1, h=7, w=9, cin=96, cout=64, k=1, residual=True),
+    dict(n=2, h=8, w=8, cin=64, cout=64, k=3, colsum=2),
+    dict(n=2, h=8, w=8, cin=64, cout=64, k=3, colsum=1, mask=True),
+    dict(n=1, h=8, w=8, cin=64, cout=32, k=3, x_cs=160, x_co=32, y_cs=160, y_co=96, relu=True),
+]
+
+
+@pytest.mark.parametrize("case", SIMT_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_conv_simt(case, dtype):
+    from srb200 import lib as L
+    out, ref, cs, _, _ = _conv_case(dtype, backend=L.BACKEND_SIMT, **case)
+    l2, mx = _rel(out, ref)
+    tol = 2e-5 if dtype == "fp32" else 6e-3
+    assert l2 < tol and mx < 4 * tol, (l2, mx)
+    if cs is not None:
+        want = ref.sum(dim=(1, 2)) if cs.shape[0] > 1 else ref.sum(dim=(0, 1, 2))[None]
+        l2c, _ = _rel(cs, want)
+        assert l2c < (1e-4 if dtype == "fp32" else 2e-2), l2c
+
+
+UMMA_CASES = [
+    dict(n=1, h=16, w=8, cin=64, cout=64, k=3),                      # exactly one tile
+    dict(n=2, h=48, w=48, cin=64, cout=64, k=3, relu=True),          # the RCAN/EDSR hot shape
+    dict(n=1, h=20, w=13, cin=64, cout=64, k=3),                     # ragged tiles (H, W not multiples)
+    dict(n=2, h=16, w=16, cin=64, cout=64, k=3, scale=0.1, residual=True),
+    dict(n=1, h=16, w=16, cin=64, cout=64, k=3, mask=True, residual=True),
+    dict(n=2, h=16, w=16, cin=64, cout=64, k=3, colsum=2),
+    dict(n=2, h=16, w=24, cin=64, cout=64, k=3, colsum=1, mask=True),
+    dict(n=1, h=16, w=16, cin=64, cout=256, k=3, shuffle=2),         # UpscaleBlock conv + PixelShuffle
+    dict(n=1, h=16, w=16, cin=256, cout=256, k=3, relu=True),        # EDSR-large (BN=128, 4 K chunks)
+    dict(n=1, h=8, w=16, cin=128, cout=576, k=3, shuffle=3),         # x3: 9 * 64
+    dict(n=1, h=16, w=16, cin=576, cout=64, k=1, residual=True),     # RDN LFF
+    dict(n=1, h=16, w=16, cin=1024, cout=64, k=1),                   # RDN GFF.0
+    dict(n=1, h=16, w=16, cin=128, cout=64, k=3, x_cs=576, x_co=0, y_cs=576, y_co=128, relu=True),  # RDN dense
+    dict(n=1, h=16, w=16, cin=64, cout=192, k=3, x_cs=576, x_co=192, y_cs=576, y_co=0, residual=False),
+    dict(n=1, h=16, w=16, cin=64, cout=32, k=3),                     # BN=32
+    dict(n=1, h=5, w=40, cin=64, cout=64, k=3),                      # short & wide -> 16x8 tiles
+]
+
+
+@pytest.mark.parametrize("case", UMMA_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_conv_umma(case):
+    from srb200 import lib as L
+    out, ref, cs, _, _ = _conv_case("bf16", backend=L.BACKEND_UMMA, **case)
+    l2, mx = _rel(out, ref)
+    assert l2 < 6e-3 and mx < 2e-2, (l2, mx)
+    if cs is not None:
+        want = ref.sum(dim=(1, 2)) if cs.shape[0] > 1 else ref.sum(dim=(0, 1, 2))[None]
+        l2c, _ = _rel(cs, want)
+        assert l2c < 2e-2, l2c
+
+
+@pytest.mark.parametrize("shuffle", [0, 2])
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_conv_dgrad_matches_autograd(dtype, shuffle):
+    """DGRAD packing: the forward kernel with rotated/swapped weights gives autograd's input grad."""
+    from srb200 import lib as L, ops
+    g = torch.Generator().manual_seed(1)
+    n, h, w, cin, cout, k = 2, 16, 16, 64, 64 if not shuffle else 256, 3
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    wt = torch.randn(cout, cin, k, k, generator=g) / (cin * 9) ** 0.5
+    r = shuffle if shuffle else 1
+    gy = torch.randn(n, h * r, w * r, cout // (r * r), generator=g).to(tdt)
+    x = torch.zeros(n, cin, h, w, dtype=torch.float64, requires_grad=True)
+    wq = wt.to(tdt).double() if dtype == "bf16" else wt.double()
+    y = F.conv2d(x, wq, padding=1)
+    if shuffle:
+        y = F.pixel_shuffle(y, r)
+    y.backward(_nchw(gy.double()))
+    ref = _nhwc(x.grad)
+    dev = _dev()
+    packs = ops.PackedWeights()
+    dx = torch.empty(n, h, w, cin, dtype=tdt, device=dev)
+    gyd = gy.to(dev)
+    if shuffle:
+        gu = ops.pixel_unshuffle(gyd, r)
+        ops.conv_dgrad_shuffled(gu, packs, wt.to(dev), dx, r)
+    else:
+        ops.conv(gyd, 0, cout, packs, wt.to(dev), None, dx, 0, cin, k, mode=L.PACK_DGRAD)
+    torch.cuda.synchronize()
+    l2, mx = _rel(dx.float(), ref)
+    assert l2 < (2e-5 if dtype == "fp32" else 6e-3), (l2, mx)
+
+
+WGRAD_CASES = [
+    dict(n=2, h=16, w=16, cin=64, cout=64, k=3),
+    dict(n=1, h=9, w=11, cin=3, cout=64, k=3),
+    dict(n=2, h=12, w=12, cin=64, cout=3, k=3),
+    dict(n=1, h=10, w=10, cin=3, cout=64, k=9),
+    dict(n=1, h=8, w=8, cin=96, cout=64, k=1),
+    dict(n=1, h=8, w=8, cin=64, cout=256, k=3, shuffle=2),
+    dict(n=1, h=8, w=8, cin=64, cout=64, k=3, alpha=0.1, accumulate=True),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_conv_wgrad(case, dtype):
+    from srb200 import ops
+    c = dict(case)
+    n, h, w, cin, cout, k = c["n"], c["h"], c["w"], c["cin"], c["cout"], c["k"]
+    shuffle, alpha, accumulate = c.get("shuffle", 0), c.get("alpha", 1.0), c.get("accumulate", False)
+    g = torch.Generator().manual_seed(2)
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    x = torch.randn(n, h, w, cin, generator=g).to(tdt)
+    r = shuffle if shuffle else 1
+    gy = torch.randn(n, h * r, w * r, cout // (r * r), generator=g).to(tdt)
+    wt = torch.zeros(cout, cin, k, k, dtype=torch.float64, requires_grad=True)
+    bt = torch.zeros(cout, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(_nchw(x.double()), wt, bt, padding=k // 2)
+    if shuffle:
+        y = F.pixel_shuffle(y, r)
+    y.backward(_nchw(gy.double()))
+    dev = _dev()
+    base = torch.randn(cout, cin, k, k, generator=g)
+    dw = base.to(dev).clone() if accumulate else torch.full((cout, cin, k, k), 3.0, device=dev)
+    db = torch.zeros(cout, device=dev) if accumulate else torch.full((cout,), 3.0, device=dev)
+    gyd = gy.to(dev)
+    if shuffle:
+        gyd = ops.pixel_unshuffle(gyd, r)
+    ops.conv_wgrad(x.to(dev), 0, cin, gyd, 0, cout, k, dw, db, accumulate=accumulate, shuffle=shuffle, alpha=alpha)
+    torch.cuda.synchronize()
+    want_w = wt.grad * alpha + (base.double() if accumulate else 0)
+    want_b = bt.grad * alpha
+    l2w, _ = _rel(dw, want_w)
+    l2b, _ = _rel(db, want_b)
+    assert l2w < 2e-5 and l2b < 2e-5, (l2w, l2b)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("compute_pool", [True, False])
+def test_channel_attention_fwd_bwd(dtype, compute_pool):
+    from srb200 import ops
+    g = torch.Generator().manual_seed(3)
+    n, h, w, c, cr = 3, 12, 10, 64, 4
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    t = torch.randn(n, h, w, c, generator=g).to(tdt)
+    skip = torch.randn(n, h, w, c, generator=g).to(tdt)
+    w1 = torch.randn(cr, c, generator=g) * 0.3
+    b1 = torch.randn(cr, generator=g) * 0.1
+    w2 = torch.randn(c, cr, generator=g) * 0.3
+    b2 = torch.randn(c, generator=g) * 0.1
+    gout = torch.randn(n, h, w, c, generator=g).to(tdt)
+    # fp64 definition (rcan.py:23-29, :54)
+    td = t.double().requires_grad_(True)
+    prm = [p.double().requires_grad_(True) for p in (w1, b1, w2, b2)]
+    s = td.mean(dim=(1, 2))
+    z = (s @ prm[0].T + prm[1]).relu()
+    yg = torch.sigmoid(z @ prm[2].T + prm[3])
+    out_ref = td * yg[:, None, None, :] + skip.double()
+    out_ref.backward(gout.double())
+    dev = _dev()
+    td_, sk_ = t.to(dev), skip.to(dev)
+    pool = torch.zeros(n, c, device=dev)
+    if not compute_pool:
+        pool = t.float().sum(dim=(1, 2)).to(dev)
+    out = torch.empty_like(td_)
+    s_out = torch.empty(n, c, device=dev)
+    y_out = torch.empty(n, c, device=dev)
+    pw = [p.to(dev).contiguous() for p in (w1, b1, w2, b2)]
+    ops.ca_fwd(td_, sk_, pool, compute_pool, *pw, out, s_out, y_out)
+    torch.cuda.synchronize()
+    tol = 1e-5 if dtype == "fp32" else 6e-3
+    assert _rel(out.float(), out_ref.detach())[0] < tol
+    assert _rel(s_out, s.detach())[0] < 1e-5
+    assert _rel(y_out, yg.detach())[0] < 1e-5
+    dt = torch.empty_like(td_)
+    dws = [torch.full_like(p, 5.0) for p in pw]
+    colsum_dt = torch.full((c,), 5.0, device=dev)
+    scratch = torch.empty(n, c, device=dev)
+    ops.ca_bwd(gout.to(dev), td_, s_out, y_out, *pw, dt, dws[0], dws[1], dws[2], dws[3], colsum_dt, scratch)
+    torch.cuda.synchronize()
+    assert _rel(dt.float(), td.grad)[0] < tol
+    gtol = 1e-4 if dtype == "fp32" else 1e-2
+    for got, want in zip(dws, prm):
+        assert _rel(got, want.grad)[0] < gtol
+    assert _rel(colsum_dt, dt.float().sum(dim=(0, 1, 2)))[0] < 1e-4
+
+
+def test_layout_and_elementwise():
+    from srb200 import ops
+    g = torch.Generator().manual_seed(4)
+    dev = _dev()
+    x = torch.rand(2, 3, 7, 9, generator=g)
+    add = torch.tensor([-0.4488, -0.4371, -0.4040])
+    for dt in (torch.float32, torch.bfloat16):
+        y = ops.nchw_to_nhwc(x.to(dev), add.to(dev), dt)
+        want = (x + add[None, :, None, None]).permute(0, 2, 3, 1)
+        assert torch.equal(y.cpu(), want.to(dt))
+        back = ops.nhwc_to_nchw(y, 0, 3, (-add).to(dev))
+        assert _rel(back, y.float().cpu().permute(0, 3, 1, 2) - add[None, :, None, None])[1] < 1e-6
+    for dt in (torch.float32, torch.bfloat16):
+        a = torch.randn(2, 5, 6, 24, generator=g).to(dt).to(dev)
+        b = torch.randn(2, 5, 6, 40, generator=g).to(dt).to(dev)
+        out = torch.zeros(2, 5, 6, 16, dtype=dt, device=dev)
+        ops.add_channels(a, 8, b, 24, out, 4, 8)
+        want = (a[..., 8:16].float() + b[..., 24:32].float()).to(dt)
+        assert torch.equal(out[..., 4:12], want) and torch.all(out[..., :4] == 0) and torch.all(out[..., 12:] == 0)
+        ops.copy_channels(b, 3, out, 1, 5)   # unaligned -> scalar path
+        assert torch.equal(out[..., 1:6], b[..., 3:8])
+        m = torch.randn(2, 5, 6, 24, generator=g).to(dt).to(dev)
+        o2 = torch.empty_like(a)
+        ops.relu_bwd(a, 0, m, 0, o2, 0, 24)
+        assert torch.equal(o2, torch.where(m > 0, a, torch.zeros_like(a)))
+        gsh = torch.randn(2, 8, 12, 5, generator=g).to(dt).to(dev)
+        un = ops.pixel_unshuffle(gsh, 2)
+        ref = F.pixel_unshuffle(gsh.permute(0, 3, 1, 2).float(), 2)         # channels (c', i, j)
+        ref = ref.reshape(2, 5, 4, 4, 6).permute(0, 3, 4, 2, 1).reshape(2, 4, 6, 20)  # -> (ij, c')
+        assert torch.equal(un.float(), ref)
+        cs = torch.full((24,), 9.0, device=dev)
+        ops.colsum(a, 0, 24, cs)
+        assert _rel(cs, a.float().sum(dim=(0, 1, 2)))[0] < 1e-5
+
+
+def test_l1_loss_and_adam():
+    from srb200 import ops
+    g = torch.Generator().manual_seed(5)
+    dev = _dev()
+    sr = torch.rand(2, 3, 17, 19, generator=g)
+    hr = torch.rand(2, 3, 17, 19, generator=g)
+    hr[0, 0, 0, :5] = sr[0, 0, 0, :5]     # exact ties -> zero gradient
+    srd = sr.double().requires_grad_(True)
+    ref = F.l1_loss(srd, hr.double())
+    ref.backward()
+    loss, grad = ops.l1_loss(sr.to(dev), hr.to(dev))
+    torch.cuda.synchronize()
+    assert abs(loss.item() - ref.item()) < 1e-6
+    assert _rel(grad, srd.grad)[1] < 1e-6
+    # Adam against torch.optim.Adam for 3 steps
+    p0 = torch.randn(1000, generator=g)
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=1e-3)
+    p = p0.to(dev).clone()
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+    for step in range(1, 4):
+        gr = torch.randn(1000, generator=g)
+        p_ref.grad = gr.clone()
+        opt.step()
+        ops.inc_counter(step_dev)
+        ops.adam_step(p, (gr * 4).to(dev), m, v, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
+                      step=0, step_dev=step_dev, grad_scale=0.25)
+    torch.cuda.synchronize()
+    assert _rel(p, p_ref.detach())[1] < 1e-6
+
+
+def test_errors_are_reported_not_thrown():
+    """C ABI error contract: non-zero status + srb_last_error text -> RuntimeError in the wrapper."""
+    from srb200 import lib as L, ops
+    dev = _dev()
+    x = torch.zeros(1, 8, 8, 64, dtype=torch.bfloat16, device=dev)
+    y = torch.zeros(1, 8, 8, 64, dtype=torch.bfloat16, device=dev)
+    w = torch.zeros(64, 64, 4, 4, device=dev)
+    with pytest.raises(RuntimeError, match="kernel size"):
+        ops.conv(x, 0, 64, ops.PackedWeights(), w, None, y, 0, 64, 4)
+    w3 = torch.zeros(64, 48, 3, 3, device=dev)
+    with pytest.raises(RuntimeError, match="not eligible"):
+        ops.conv(x, 0, 48, ops.PackedWeights(), w3, None, y, 0, 64, 3, backend=L.BACKEND_UMMA)
+    with pytest.raises(RuntimeError, match="CUDA tensors"):
+        ops.nchw_to_nhwc(torch.zeros(1, 3, 4, 4), None, torch.float32)
