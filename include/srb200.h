@@ -90,6 +90,8 @@ const char* srb_last_error(void);
 int  srb_create(int device, srb_ctx** out);
 int  srb_destroy(srb_ctx* ctx);
 int  srb_num_sms(const srb_ctx* ctx);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long srb_launch_count(void);
 
 /* ---- weights ------------------------------------------------------------------------------
  * nn.Conv2d.weight is fp32 OIHW (state_dict contract).  Packed copies are caches.

@@ -13,6 +13,10 @@ void srb_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+unsigned long long g_srb_launches = 0;
+
+extern "C" unsigned long long srb_launch_count(void) { return __atomic_load_n(&g_srb_launches, __ATOMIC_RELAXED); }
+
 extern "C" int srb_abi_version(void) { return SRB_ABI_VERSION; }
 
 extern "C" const char* srb_last_error(void) { return g_err; }

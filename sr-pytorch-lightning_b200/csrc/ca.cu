@@ -14,11 +14,11 @@ static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s)
 template <typename T, bool MUL>
 __global__ void ca_reduce_kernel(const T* __restrict__ a, const T* __restrict__ b, int HW, int C,
                                  float* __restrict__ out) {
-  extern __shared__ float red[];  // [C]
+  extern __shared__ double red[];  // [C]; cross-thread sums in fp64 (the per-thread partials are short)
   const int cg = C / 4;
   const int n = blockIdx.y;
   const int g = threadIdx.x % cg, lane = threadIdx.x / cg, lanes = blockDim.x / cg;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) red[i] = 0.f;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) red[i] = 0.0;
   __syncthreads();
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (lane < lanes) {
@@ -31,13 +31,13 @@ __global__ void ca_reduce_kernel(const T* __restrict__ a, const T* __restrict__ 
       }
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    atomicAdd(&red[g * 4 + 0], acc.x);
-    atomicAdd(&red[g * 4 + 1], acc.y);
-    atomicAdd(&red[g * 4 + 2], acc.z);
-    atomicAdd(&red[g * 4 + 3], acc.w);
+    atomicAdd(&red[g * 4 + 0], (double)acc.x);
+    atomicAdd(&red[g * 4 + 1], (double)acc.y);
+    atomicAdd(&red[g * 4 + 2], (double)acc.z);
+    atomicAdd(&red[g * 4 + 3], (double)acc.w);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(out + (int64_t)n * C + i, red[i]);
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(out + (int64_t)n * C + i, (float)red[i]);
 }
 
 // gate MLP from pooled sums; every thread of the block cooperates. smem: s[C] z[Cr] y[C]
@@ -59,7 +59,7 @@ __device__ __forceinline__ void ca_gate(const float* __restrict__ sums, float in
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float u = b2[c];
     for (int j = 0; j < Cr; ++j) u += w2[c * Cr + j] * z_s[j];
-    y_s[c] = 1.f / (1.f + __expf(-u));
+    y_s[c] = 1.f / (1.f + expf(-u));
   }
   __syncthreads();
 }
@@ -101,7 +101,8 @@ template <typename T>
 __global__ void ca_bwd_apply_kernel(const T* __restrict__ g, const float* __restrict__ s, const float* __restrict__ y,
                                     const float* __restrict__ dysum, int HW, int C, int Cr,
                                     const float* __restrict__ w1, const float* __restrict__ b1,
-                                    const float* __restrict__ w2, T* __restrict__ dt, float* __restrict__ dw1,
+                                    const float* __restrict__ w2, const float* __restrict__ b2, T* __restrict__ dt,
+                                    float* __restrict__ dw1,
                                     float* __restrict__ db1, float* __restrict__ dw2, float* __restrict__ db2,
                                     float* __restrict__ colsum_dt) {
   extern __shared__ float sm[];
@@ -115,26 +116,36 @@ __global__ void ca_bwd_apply_kernel(const T* __restrict__ g, const float* __rest
   const int n = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane_w = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float yy = y[(int64_t)n * C + c];
     s_s[c] = s[(int64_t)n * C + c];
-    y_s[c] = yy;
-    du_s[c] = dysum[(int64_t)n * C + c] * yy * (1.f - yy);
+    y_s[c] = y[(int64_t)n * C + c];
     cs_s[c] = 0.f;
   }
   __syncthreads();
+  // recompute the hidden layer (needed for dW2 and the ReLU mask)
   for (int j = warp; j < Cr; j += nwarps) {
-    float v = 0.f, dz = 0.f;
-    for (int c = lane_w; c < C; c += 32) {
-      v += w1[j * C + c] * s_s[c];
-      dz += w2[c * Cr + j] * du_s[c];
-    }
+    float v = 0.f;
+    for (int c = lane_w; c < C; c += 32) v += w1[j * C + c] * s_s[c];
     v = warp_sum(v);
-    dz = warp_sum(dz);
     if (lane_w == 0) {
       v += b1[j];
       z_s[j] = fmaxf(v, 0.f);
-      dv_s[j] = v > 0.f ? dz : 0.f;
+      dv_s[j] = v > 0.f ? 1.f : 0.f;   // ReLU mask for now
     }
+  }
+  __syncthreads();
+  // sigmoid'(u) = sigmoid(u) * sigmoid(-u), from u itself: no (1 - y) cancellation near saturation
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float u = b2[c];
+    for (int j = 0; j < Cr; ++j) u += w2[c * Cr + j] * z_s[j];
+    const float sp = 1.f / (1.f + expf(-u)), sn = 1.f / (1.f + expf(u));
+    du_s[c] = dysum[(int64_t)n * C + c] * sp * sn;
+  }
+  __syncthreads();
+  for (int j = warp; j < Cr; j += nwarps) {
+    float dz = 0.f;
+    for (int c = lane_w; c < C; c += 32) dz += w2[c * Cr + j] * du_s[c];
+    dz = warp_sum(dz);
+    if (lane_w == 0) dv_s[j] *= dz;
   }
   __syncthreads();
   const float inv_hw = 1.f / (float)HW;
@@ -214,9 +225,9 @@ extern "C" int srb_ca_fwd(srb_ctx* ctx, int N, int H, int W, int C, int Cr, int 
   if (compute_pool) {
     SRB_CHECK_CUDA(cudaMemsetAsync(pooled_sum, 0, sizeof(float) * (size_t)N * C, S(stream)));
     if (dtype == SRB_F32)
-      ca_reduce_kernel<float, false><<<grid, threads, C * sizeof(float), S(stream)>>>((const float*)t, nullptr, HW, C, pooled_sum);
+      ca_reduce_kernel<float, false><<<grid, threads, C * sizeof(double), S(stream)>>>((const float*)t, nullptr, HW, C, pooled_sum);
     else
-      ca_reduce_kernel<__nv_bfloat16, false><<<grid, threads, C * sizeof(float), S(stream)>>>((const __nv_bfloat16*)t, nullptr, HW, C, pooled_sum);
+      ca_reduce_kernel<__nv_bfloat16, false><<<grid, threads, C * sizeof(double), S(stream)>>>((const __nv_bfloat16*)t, nullptr, HW, C, pooled_sum);
     SRB_LAUNCH_CHECK();
   }
   size_t smem = sizeof(float) * (2 * C + Cr);
@@ -235,8 +246,7 @@ extern "C" int srb_ca_bwd(srb_ctx* ctx, int N, int H, int W, int C, int Cr, int 
                           const float* s, const float* y, const float* w1, const float* b1, const float* w2,
                           const float* b2, void* dt, float* dw1, float* db1, float* dw2, float* db2, float* colsum_dt,
                           float* scratch, int accumulate, void* stream) {
-  (void)b2;
-  SRB_REQUIRE(ctx && g && t && s && y && w1 && b1 && w2 && dt && dw1 && db1 && dw2 && db2 && scratch,
+  SRB_REQUIRE(ctx && g && t && s && y && w1 && b1 && w2 && b2 && dt && dw1 && db1 && dw2 && db2 && scratch,
               "srb_ca_bwd: null argument");
   SRB_REQUIRE(C % 4 == 0 && C <= 1024 && Cr >= 1 && Cr <= 64, "srb_ca_bwd: unsupported C=%d Cr=%d", C, Cr);
   const int HW = H * W;
@@ -254,16 +264,16 @@ extern "C" int srb_ca_bwd(srb_ctx* ctx, int N, int H, int W, int C, int Cr, int 
   }
   size_t smem = sizeof(float) * (5 * C + 2 * Cr);
   if (dtype == SRB_F32) {
-    ca_reduce_kernel<float, true><<<grid, threads, C * sizeof(float), st>>>((const float*)g, (const float*)t, HW, C, scratch);
+    ca_reduce_kernel<float, true><<<grid, threads, C * sizeof(double), st>>>((const float*)g, (const float*)t, HW, C, scratch);
     SRB_LAUNCH_CHECK();
-    ca_bwd_apply_kernel<float><<<grid, threads, smem, st>>>((const float*)g, s, y, scratch, HW, C, Cr, w1, b1, w2,
+    ca_bwd_apply_kernel<float><<<grid, threads, smem, st>>>((const float*)g, s, y, scratch, HW, C, Cr, w1, b1, w2, b2,
                                                             (float*)dt, dw1, db1, dw2, db2, colsum_dt);
   } else {
-    ca_reduce_kernel<__nv_bfloat16, true><<<grid, threads, C * sizeof(float), st>>>((const __nv_bfloat16*)g,
+    ca_reduce_kernel<__nv_bfloat16, true><<<grid, threads, C * sizeof(double), st>>>((const __nv_bfloat16*)g,
                                                                                      (const __nv_bfloat16*)t, HW, C, scratch);
     SRB_LAUNCH_CHECK();
     ca_bwd_apply_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>((const __nv_bfloat16*)g, s, y, scratch, HW, C, Cr, w1,
-                                                                    b1, w2, (__nv_bfloat16*)dt, dw1, db1, dw2, db2, colsum_dt);
+                                                                    b1, w2, b2, (__nv_bfloat16*)dt, dw1, db1, dw2, db2, colsum_dt);
   }
   SRB_LAUNCH_CHECK();
   return 0;

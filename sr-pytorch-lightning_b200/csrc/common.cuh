@@ -34,7 +34,12 @@ void srb_set_error(const char* fmt, ...);
     }                             \
   } while (0)
 
-#define SRB_LAUNCH_CHECK() SRB_CHECK_CUDA(cudaGetLastError())
+extern unsigned long long g_srb_launches;  // kernels launched by this library (bench.py's gpu_launches)
+#define SRB_LAUNCH_CHECK()                   \
+  do {                                       \
+    __atomic_fetch_add(&g_srb_launches, 1ull, __ATOMIC_RELAXED); \
+    SRB_CHECK_CUDA(cudaGetLastError());      \
+  } while (0)
 
 static inline int srb_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

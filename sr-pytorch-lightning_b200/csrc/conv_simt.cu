@@ -76,6 +76,13 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
         w_s[idx] = v;
       }
       __syncthreads();
+      // two-level summation: a short inner partial sum per (channel chunk, kh), folded into the
+      // running accumulator, keeps the fp32 rounding error ~sqrt(K/48) instead of ~sqrt(K)
+      float part[4][4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) part[p][c] = 0.f;
 #pragma unroll 4
       for (int c = 0; c < CK; ++c) {
         float xin[4 + K - 1];
@@ -86,13 +93,17 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
           float4 wv = *reinterpret_cast<const float4*>(&w_s[(kw * CK + c) * CO_T + tx * 4]);
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
-            acc[p][0] = fmaf(xin[p + kw], wv.x, acc[p][0]);
-            acc[p][1] = fmaf(xin[p + kw], wv.y, acc[p][1]);
-            acc[p][2] = fmaf(xin[p + kw], wv.z, acc[p][2]);
-            acc[p][3] = fmaf(xin[p + kw], wv.w, acc[p][3]);
+            part[p][0] = fmaf(xin[p + kw], wv.x, part[p][0]);
+            part[p][1] = fmaf(xin[p + kw], wv.y, part[p][1]);
+            part[p][2] = fmaf(xin[p + kw], wv.z, part[p][2]);
+            part[p][3] = fmaf(xin[p + kw], wv.w, part[p][3]);
           }
         }
       }
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[p][c] += part[p][c];
     }
   }
 
@@ -246,6 +257,12 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradArgs a) {
       x_s[c][r][q] = v;
     }
     __syncthreads();
+    float part[K][4];  // per-tile partial sums (two-level summation, see conv kernel)
+    float bpart[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kw = 0; kw < K; ++kw)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) part[kw][c] = 0.f;
 #pragma unroll 4
     for (int p = 0; p < TS * TS; ++p) {
       const int r = p / TS, c = p % TS;
@@ -253,15 +270,21 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradArgs a) {
 #pragma unroll
       for (int kw = 0; kw < K; ++kw) {
         float xv = x_s[ty][r][c + kw];
-        acc[kw][0] = fmaf(g4.x, xv, acc[kw][0]);
-        acc[kw][1] = fmaf(g4.y, xv, acc[kw][1]);
-        acc[kw][2] = fmaf(g4.z, xv, acc[kw][2]);
-        acc[kw][3] = fmaf(g4.w, xv, acc[kw][3]);
+        part[kw][0] = fmaf(g4.x, xv, part[kw][0]);
+        part[kw][1] = fmaf(g4.y, xv, part[kw][1]);
+        part[kw][2] = fmaf(g4.z, xv, part[kw][2]);
+        part[kw][3] = fmaf(g4.w, xv, part[kw][3]);
       }
       if (do_bias) {
-        bsum[0] += g4.x; bsum[1] += g4.y; bsum[2] += g4.z; bsum[3] += g4.w;
+        bpart[0] += g4.x; bpart[1] += g4.y; bpart[2] += g4.z; bpart[3] += g4.w;
       }
     }
+#pragma unroll
+    for (int kw = 0; kw < K; ++kw)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[kw][c] += part[kw][c];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) bsum[c] += bpart[c];
   }
 
   const int rr = d.shuffle > 1 ? d.shuffle * d.shuffle : 1;

@@ -41,6 +41,7 @@ PROTOTYPES = {
     "srb_create": (c_i32, [c_i32, C.POINTER(c_vp)]),
     "srb_destroy": (c_i32, [c_vp]),
     "srb_num_sms": (c_i32, [c_vp]),
+    "srb_launch_count": (C.c_ulonglong, []),
     "srb_packed_weight_bytes": (C.c_size_t, [c_i32, c_i32, c_i32, c_i32, c_i32]),
     "srb_pack_weight": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "srb_pack_bias": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
@@ -97,6 +98,10 @@ def last_error() -> str:
 def check(rc: int, what: str = ""):
     if rc != 0:
         raise RuntimeError(f"libsrb200 {what} failed (code {rc}): {last_error()}")
+
+
+def launch_count() -> int:
+    return int(load().srb_launch_count())
 
 
 def ctx(device_index: int) -> int:

@@ -64,6 +64,16 @@ def pack_bias(b: torch.Tensor, shuffle: int) -> torch.Tensor:
     return out
 
 
+_generation = 0
+
+
+def invalidate_packed():
+    """Mark every packed-weight cache stale (parameters were updated by a kernel that does not
+    bump tensor versions, e.g. the flat Adam step)."""
+    global _generation
+    _generation += 1
+
+
 class PackedWeights:
     """Cache of packed copies of one conv weight, rebuilt when the parameter changes
     (keyed on data_ptr and the tensor version counter, SURVEY §8b "Ownership")."""
@@ -73,7 +83,7 @@ class PackedWeights:
 
     def get(self, w: torch.Tensor, packing: int, mode: int, shuffle: int = 0):
         key = (packing, mode, shuffle)
-        tag = (w.data_ptr(), w._version, w.device)
+        tag = (w.data_ptr(), w._version, w.device, _generation)
         hit = self._cache.get(key)
         if hit is not None and hit[0] == tag:
             return hit[1]
@@ -85,7 +95,7 @@ class PackedWeights:
         if b is None or shuffle <= 1:
             return b.detach() if b is not None else None
         key = ("bias", shuffle)
-        tag = (b.data_ptr(), b._version, b.device)
+        tag = (b.data_ptr(), b._version, b.device, _generation)
         hit = self._cache.get(key)
         if hit is not None and hit[0] == tag:
             return hit[1]

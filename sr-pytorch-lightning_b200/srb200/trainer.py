@@ -1,0 +1,135 @@
+"""Training-step runner for the B200 path: flat parameter / gradient / Adam-state buffers, one
+CUDA graph per step (forward + L1 + backward + gradient all-reduce + Adam), data-parallel over
+`torch.distributed` (one process per GPU, NCCL over NVLink).
+
+What it replaces in the reference: Lightning's fit loop around `SRModel.training_step`
+(/root/reference/models/srmodel.py:160-171), `configure_optimizers` (srmodel.py:145-154, Adam
+defaults) and the implicit DDP gradient all-reduce.  Python runs once, at capture;
+a replayed step is a single `cudaGraphLaunch` — the >5000 eager launches per RCAN step the
+reference issues never touch the host again.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import functional as F200
+from . import ops
+
+
+class FlatParams:
+    """Re-homes every trainable parameter of `model` into one contiguous fp32 buffer (16-byte
+    aligned slices) with matching flat gradient and Adam-moment buffers.  `state_dict()` is
+    unaffected (parameters become views).  Installs `_srb_grad` views so the backward kernels
+    write gradients in place (srb200.functional._grad_target)."""
+
+    def __init__(self, model: torch.nn.Module):
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        if not self.params:
+            raise ValueError("model has no trainable parameters")
+        dev = self.params[0].device
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        self.numel = total
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        with torch.no_grad():
+            for p, o in zip(self.params, offs):
+                view = self.flat[o:o + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                p._srb_grad = self.grad[o:o + p.numel()].view_as(p)
+                p._srb_grad_live = False
+        self.offsets = offs
+
+    def begin_step(self):
+        """First gradient write of a step overwrites, later ones accumulate: no zero-fill pass."""
+        for p in self.params:
+            p._srb_grad_live = False
+
+    def grads_by_name(self, model):
+        return {k: p._srb_grad for k, p in model.named_parameters() if p.requires_grad}
+
+    def detach(self):
+        for p in self.params:
+            if hasattr(p, "_srb_grad"):
+                del p._srb_grad
+                del p._srb_grad_live
+
+
+class TrainStep:
+    """One training step of an SRModel subclass on fixed-shape batches.
+
+    step(lr_batch, hr_batch) -> loss tensor (device).  Inputs may be host (pinned) or device
+    tensors; they are copied into static device buffers, then the captured graph is replayed."""
+
+    def __init__(self, model, lr_shape, scale: int, *, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0, use_graph: bool = True, process_group=None):
+        self.model = model
+        self.flat = FlatParams(model)
+        dev = self.flat.flat.device
+        n, c, h, w = lr_shape
+        self.x = torch.zeros(lr_shape, dtype=torch.float32, device=dev)
+        self.hr = torch.zeros((n, c, h * scale, w * scale), dtype=torch.float32, device=dev)
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.hp = dict(lr=lr, beta1=betas[0], beta2=betas[1], eps=eps, weight_decay=weight_decay)
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.use_graph = use_graph
+        self.graph = None
+        self.launches_per_step = 0
+
+    # the work of one step; captured once
+    def _body(self):
+        self.flat.begin_step()
+        ops.invalidate_packed()                       # weights changed: re-pack inside the step
+        sr = self.model.forward(self.x)
+        loss = F200.l1_loss(sr, self.hr)
+        loss.backward()
+        if self.world > 1:
+            dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.pg)
+        ops.inc_counter(self.flat.step_dev)
+        ops.adam_step(self.flat.flat, self.flat.grad, self.flat.m, self.flat.v, step=0, step_dev=self.flat.step_dev,
+                      grad_scale=1.0 / self.world, **self.hp)
+        self.loss.copy_(loss.detach())
+
+    def capture(self, warmup: int = 2):
+        from . import lib as L
+        if not self.use_graph:
+            return
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        c0 = L.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body()
+        self.launches_per_step = L.launch_count() - c0
+        torch.cuda.synchronize()
+
+    def load_batch(self, lr_batch, hr_batch):
+        self.x.copy_(lr_batch, non_blocking=True)
+        self.hr.copy_(hr_batch, non_blocking=True)
+
+    def run(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            from . import lib as L
+            c0 = L.launch_count()
+            self._body()
+            self.launches_per_step = L.launch_count() - c0
+        return self.loss
+
+    def step(self, lr_batch, hr_batch):
+        self.load_batch(lr_batch, hr_batch)
+        return self.run()
