@@ -103,6 +103,15 @@ int  srb_pack_weight(srb_ctx*, const float* w_oihw, int Cout, int Cin, int ksize
                      int shuffle, void* out, void* stream);
 /* bias permuted the same way as the packed output channels (fp32 [Cout]) */
 int  srb_pack_bias(srb_ctx*, const float* bias, int Cout, int shuffle, float* out, void* stream);
+/* Re-pack MANY weights in one launch (after an optimizer step): `table` is a DEVICE array of n
+ * items, built once because parameter and packed-buffer addresses are stable.  ksize == 0 marks a
+ * bias item (srb_pack_bias semantics).  max_elems = largest Cout*Cin*k*k in the table. */
+typedef struct srb_pack_item {
+  const float* src;
+  void* dst;
+  int32_t Cout, Cin, ksize, packing, mode, shuffle;
+} srb_pack_item;
+int  srb_pack_table(srb_ctx*, const srb_pack_item* table_dev, int n, int64_t max_elems, void* stream);
 
 /* ---- convolution --------------------------------------------------------------------------
  * Replaces nn.Conv2d.forward at every call site of models/common.py:7-30 (DefaultConv2d),
@@ -116,6 +125,16 @@ int  srb_conv(srb_ctx*, const srb_conv_desc*, const void* x, const void* w_packe
  * dbias fp32 [Cout] (may be NULL). */
 int  srb_conv_wgrad(srb_ctx*, const srb_wgrad_desc*, const void* x, const void* gy,
                     float* dw_oihw, float* dbias, void* stream);
+/* Many weight gradients in one call (the backward pass defers them: they are off the critical
+ * path of the input-gradient chain).  Eligible layers share batched tcgen05 launches. */
+typedef struct srb_wgrad_item {
+  srb_wgrad_desc d;
+  const void* x;
+  const void* gy;
+  float* dw;
+  float* dbias;             /* may be NULL */
+} srb_wgrad_item;
+int  srb_conv_wgrad_batched(srb_ctx*, const srb_wgrad_item* items, int n, void* stream);
 /* which kernel family (and hence which weight packing) backend AUTO resolves to */
 int  srb_conv_uses_umma(const srb_conv_desc*);
 int  srb_wgrad_uses_umma(const srb_wgrad_desc*);
@@ -131,12 +150,13 @@ int  srb_ca_fwd(srb_ctx*, int N, int H, int W, int C, int Cr, int dtype,
                 void* out, float* s_out, float* y_out, void* stream);
 /* backward: g = dL/dout.  dt = g*y + broadcast(ds)/HW; parameter grads are accumulated (+=)
  * when accumulate != 0, else overwritten.  colsum_dt (nullable): per-channel sums of dt over
- * N,H,W = bias gradient of the conv that produced t.  scratch: [N][C] fp32. */
+ * N,H,W = bias gradient of the conv that produced t.  scratch: [N][C] fp32, zero-filled here
+ * unless scratch_is_zero (the caller hands out slices of one arena it cleared once per step). */
 int  srb_ca_bwd(srb_ctx*, int N, int H, int W, int C, int Cr, int dtype,
                 const void* g, const void* t, const float* s, const float* y,
                 const float* w1, const float* b1, const float* w2, const float* b2,
                 void* dt, float* dw1, float* db1, float* dw2, float* db2,
-                float* colsum_dt, float* scratch, int accumulate, void* stream);
+                float* colsum_dt, float* scratch, int scratch_is_zero, int accumulate, void* stream);
 
 /* ---- boundary layout conversion (model input / output only) --------------------------------
  * NCHW fp32 (what SRModel.forward receives, srmodel.py:163) <-> NHWC dtype, with MeanShift

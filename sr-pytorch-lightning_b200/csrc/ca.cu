@@ -245,7 +245,7 @@ extern "C" int srb_ca_fwd(srb_ctx* ctx, int N, int H, int W, int C, int Cr, int 
 extern "C" int srb_ca_bwd(srb_ctx* ctx, int N, int H, int W, int C, int Cr, int dtype, const void* g, const void* t,
                           const float* s, const float* y, const float* w1, const float* b1, const float* w2,
                           const float* b2, void* dt, float* dw1, float* db1, float* dw2, float* db2, float* colsum_dt,
-                          float* scratch, int accumulate, void* stream) {
+                          float* scratch, int scratch_is_zero, int accumulate, void* stream) {
   SRB_REQUIRE(ctx && g && t && s && y && w1 && b1 && w2 && b2 && dt && dw1 && db1 && dw2 && db2 && scratch,
               "srb_ca_bwd: null argument");
   SRB_REQUIRE(C % 4 == 0 && C <= 1024 && Cr >= 1 && Cr <= 64, "srb_ca_bwd: unsupported C=%d Cr=%d", C, Cr);
@@ -254,7 +254,7 @@ extern "C" int srb_ca_bwd(srb_ctx* ctx, int N, int H, int W, int C, int Cr, int 
   const int slabs = ca_slabs(ctx, N, HW, threads, C);
   dim3 grid(slabs, N);
   cudaStream_t st = S(stream);
-  SRB_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * (size_t)N * C, st));
+  if (!scratch_is_zero) SRB_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * (size_t)N * C, st));
   if (!accumulate) {
     SRB_CHECK_CUDA(cudaMemsetAsync(dw1, 0, sizeof(float) * (size_t)C * Cr, st));
     SRB_CHECK_CUDA(cudaMemsetAsync(dw2, 0, sizeof(float) * (size_t)C * Cr, st));

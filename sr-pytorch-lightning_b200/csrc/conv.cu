@@ -1,4 +1,6 @@
 // Dispatch of the convolution entry points (include/srb200.h) to the tcgen05 or CUDA-core kernels.
+#include <vector>
+
 #include "common.cuh"
 
 int srb_conv_simt(srb_ctx*, const srb_conv_desc*, const void*, const void*, const float*, const void*, const void*,
@@ -9,6 +11,9 @@ int srb_conv_umma_bn(const srb_conv_desc*);
 int srb_wgrad_simt(srb_ctx*, const srb_wgrad_desc*, const void*, const void*, float*, float*, cudaStream_t);
 int srb_wgrad_umma(srb_ctx*, const srb_wgrad_desc*, const void*, const void*, float*, float*, cudaStream_t);
 int srb_wgrad_umma_ok(const srb_wgrad_desc*);
+int srb_wgrad_umma_batched(srb_ctx*, const srb_wgrad_desc*, const void* const*, const void* const*, float* const*, int,
+                           cudaStream_t);
+int srb_colsum_launch(srb_ctx*, const void*, int, int, int, int64_t, int, float*, int, float, int, cudaStream_t);
 
 static int check_conv_desc(const srb_conv_desc* d, const void* x, const void* w, const void* res, const void* mask,
                            void* y, void* y2, float* colsum) {
@@ -67,4 +72,36 @@ extern "C" int srb_conv_wgrad(srb_ctx* ctx, const srb_wgrad_desc* d, const void*
 extern "C" int srb_wgrad_uses_umma(const srb_wgrad_desc* d) {
   if (!d || d->backend == SRB_BACKEND_SIMT) return 0;
   return srb_wgrad_umma_ok(d);
+}
+
+/* Many weight gradients in one call: the tcgen05-eligible ones share batched launches (one CTA per
+ * 64x64x9 block, whole pixel reduction per CTA — see wgrad_umma.cu), the rest go to the CUDA-core
+ * kernel one by one. */
+extern "C" int srb_conv_wgrad_batched(srb_ctx* ctx, const srb_wgrad_item* items, int n, void* stream) {
+  SRB_REQUIRE(ctx && (items || n == 0), "srb_conv_wgrad_batched: null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  std::vector<srb_wgrad_desc> descs;
+  std::vector<const void*> xs, gys;
+  std::vector<float*> dws;
+  for (int i = 0; i < n; ++i) {
+    const srb_wgrad_item& it = items[i];
+    SRB_REQUIRE(it.x && it.gy && it.dw, "srb_conv_wgrad_batched: item %d has a null pointer", i);
+    const bool umma = it.d.backend != SRB_BACKEND_SIMT && srb_wgrad_umma_ok(&it.d);
+    if (umma) {
+      descs.push_back(it.d);
+      xs.push_back(it.x);
+      gys.push_back(it.gy);
+      dws.push_back(it.dw);
+      if (it.dbias) {
+        int rc = srb_colsum_launch(ctx, it.gy, it.d.g_cs, it.d.g_co, it.d.Cout, (int64_t)it.d.N * it.d.H * it.d.W,
+                                   it.d.dtype, it.dbias, it.d.accumulate, it.d.alpha, it.d.shuffle, st);
+        if (rc) return rc;
+      }
+    } else {
+      int rc = srb_conv_wgrad(ctx, &it.d, it.x, it.gy, it.dw, it.dbias, stream);
+      if (rc) return rc;
+    }
+  }
+  if (descs.empty()) return 0;
+  return srb_wgrad_umma_batched(ctx, descs.data(), xs.data(), gys.data(), dws.data(), (int)descs.size(), st);
 }

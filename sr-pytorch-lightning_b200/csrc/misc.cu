@@ -306,7 +306,8 @@ extern "C" int srb_relu_bwd(srb_ctx* ctx, const void* g, int g_cs, int g_co, con
 // per-channel sums
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void colsum_kernel(const T* __restrict__ x, int cs, int co, int C, int64_t npix, float* __restrict__ out) {
+__global__ void colsum_kernel(const T* __restrict__ x, int cs, int co, int C, int64_t npix, float* __restrict__ out,
+                              float alpha, int shuffle) {
   // blockDim = (32 channels, 8 pixel lanes); grid.x over channel groups of 32, grid.y over pixel slabs
   __shared__ float red[8][33];
   int c = blockIdx.x * 32 + threadIdx.x;
@@ -321,25 +322,36 @@ __global__ void colsum_kernel(const T* __restrict__ x, int cs, int co, int C, in
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
-    atomicAdd(out + c, s);
+    int oc = c;  // x is in (ij, c') channel order when it is an un-shuffled gradient
+    if (shuffle > 1) {
+      int rr = shuffle * shuffle, Cp = C / rr;
+      oc = (c % Cp) * rr + c / Cp;
+    }
+    atomicAdd(out + oc, s * alpha);
   }
 }
 
-extern "C" int srb_colsum(srb_ctx* ctx, const void* x, int cs, int co, int C, int64_t npix, int dtype, float* out,
-                          int accumulate, void* stream) {
-  SRB_REQUIRE(ctx && x && out, "srb_colsum: null argument");
-  if (!accumulate) SRB_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, S(stream)));
+int srb_colsum_launch(srb_ctx* ctx, const void* x, int cs, int co, int C, int64_t npix, int dtype, float* out,
+                      int accumulate, float alpha, int shuffle, cudaStream_t st) {
+  (void)ctx;
+  if (!accumulate) SRB_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
   dim3 block(32, 8);
   int slabs = srb_cdiv(npix, 8 * 64);
   if (slabs > 512) slabs = 512;
   if (slabs < 1) slabs = 1;
   dim3 grid(srb_cdiv(C, 32), slabs);
   if (dtype == SRB_F32)
-    colsum_kernel<float><<<grid, block, 0, S(stream)>>>((const float*)x, cs, co, C, npix, out);
+    colsum_kernel<float><<<grid, block, 0, st>>>((const float*)x, cs, co, C, npix, out, alpha, shuffle);
   else
-    colsum_kernel<__nv_bfloat16><<<grid, block, 0, S(stream)>>>((const __nv_bfloat16*)x, cs, co, C, npix, out);
+    colsum_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, cs, co, C, npix, out, alpha, shuffle);
   SRB_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int srb_colsum(srb_ctx* ctx, const void* x, int cs, int co, int C, int64_t npix, int dtype, float* out,
+                          int accumulate, void* stream) {
+  SRB_REQUIRE(ctx && x && out, "srb_colsum: null argument");
+  return srb_colsum_launch(ctx, x, cs, co, C, npix, dtype, out, accumulate, 1.0f, 0, S(stream));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -418,6 +430,59 @@ extern "C" int srb_adam_step(srb_ctx* ctx, float* param, const float* grad, floa
   if (blocks < 1) blocks = 1;
   adam_kernel<<<blocks, 256, 0, S(stream)>>>(param, grad, m, v, n, lr, beta1, beta2, eps, weight_decay, step, step_dev,
                                              grad_scale);
+  SRB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// table-driven re-pack of all conv weights of a model in ONE launch (per optimizer step)
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_table_kernel(const srb_pack_item* __restrict__ table) {
+  const srb_pack_item it = table[blockIdx.y];
+  const int k = it.ksize;
+  if (k == 0) {  // bias
+    for (int co = blockIdx.x * blockDim.x + threadIdx.x; co < it.Cout; co += gridDim.x * blockDim.x)
+      reinterpret_cast<float*>(it.dst)[perm_channel(co, it.Cout, it.shuffle)] = it.src[co];
+    return;
+  }
+  const int Cout = it.Cout, Cin = it.Cin;
+  const int64_t total = (int64_t)Cout * Cin * k * k;
+  const int rr = it.shuffle > 1 ? it.shuffle * it.shuffle : 1;
+  (void)rr;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int kw = i % k;
+    const int kh = (i / k) % k;
+    const int ci = (i / (k * k)) % Cin;
+    const int co = i / ((int64_t)k * k * Cin);
+    const int cop = perm_channel(co, Cout, it.shuffle);
+    const float v = it.src[i];
+    if (it.packing == SRB_PACK_SIMT) {
+      float* out = reinterpret_cast<float*>(it.dst);
+      if (it.mode == SRB_PACK_FWD) out[(((int64_t)kh * k + kw) * Cin + ci) * Cout + cop] = v;
+      else out[(((int64_t)(k - 1 - kh) * k + (k - 1 - kw)) * Cout + cop) * Cin + ci] = v;
+    } else {
+      // UMMA layout [chunk][kw][kh][row][64] of the effective conv (zero padding of a partial last
+      // chunk was written when the buffer was first packed and never changes)
+      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(it.dst);
+      if (it.mode == SRB_PACK_FWD) {
+        const int chunk = ci >> 6, kk = ci & 63;
+        out[((((int64_t)chunk * k + kw) * k + kh) * Cout + cop) * 64 + kk] = __float2bfloat16_rn(v);
+      } else {
+        const int chunk = cop >> 6, kk = cop & 63;
+        out[((((int64_t)chunk * k + (k - 1 - kw)) * k + (k - 1 - kh)) * Cin + ci) * 64 + kk] = __float2bfloat16_rn(v);
+      }
+    }
+  }
+}
+
+extern "C" int srb_pack_table(srb_ctx* ctx, const srb_pack_item* table_dev, int n, int64_t max_elems, void* stream) {
+  SRB_REQUIRE(ctx && (table_dev || n == 0), "srb_pack_table: null argument");
+  if (n == 0) return 0;
+  SRB_REQUIRE(n <= 65535, "srb_pack_table: too many items (%d)", n);
+  int bx = srb_cdiv(max_elems, 256 * 4);
+  if (bx < 1) bx = 1;
+  if (bx > 64) bx = 64;
+  pack_table_kernel<<<dim3(bx, n), 256, 0, S(stream)>>>(table_dev);
   SRB_LAUNCH_CHECK();
   return 0;
 }

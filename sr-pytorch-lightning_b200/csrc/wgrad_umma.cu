@@ -1,10 +1,301 @@
-// tcgen05 weight-gradient kernel (placeholder until the MN-major split-K kernel lands: reports
-// "not eligible" so the dispatcher uses the CUDA-core kernel).
+// Weight gradient of 3x3 convolutions on tcgen05 tensor cores (sm_100a).
+//
+//   dW[co][ci][kh][kw] = alpha * sum_{n,h,w} gy[n,h,w,co] * x[n,h+kh-1,w+kw-1,ci]
+//
+// GEMM view per filter tap: D_tap[ci, co] = sum_pixels X_tap[pixel, ci] * G[pixel, co].  The
+// reduction index is the PIXEL, and NHWC keeps channels contiguous, so both operands are
+// "MN-major": one 128-byte line = 64 channels of one pixel, 8 pixels = one 1024-byte swizzle atom
+// along K.  The same TMA-written tiles the forward kernel uses serve as both operands.
+//
+// Work unit ("block") = 64 input channels x 64 output channels x 9 taps of one layer.  The 9 taps
+// are stacked in pairs along M (UMMA M = 128 = 2 taps x 64 ci; the second tap is just a different
+// start address, i.e. the descriptor's leading-dim byte offset), giving 5 accumulators of 64 fp32
+// TMEM columns.  A CTA owns a block (or 1/S of its pixels), walks its 128-pixel tiles with a
+// 3-stage TMA ring and keeps accumulating in TMEM; only at the very end does it touch global
+// memory: plain stores when it owns the whole reduction (S = 1), red.global.add otherwise.
+//
+// Many layers are batched into ONE launch (their tensor maps travel as kernel parameters): with a
+// whole reduction per CTA there is no split-K traffic at all, and 148 CTAs stay busy even though
+// one layer's dW is only 64x64x9.  The backward pass defers its weight gradients into such batches
+// (srb200/functional.py WgradQueue): they are off the critical path of the dgrad chain.
+#include <vector>
+
 #include "common.cuh"
+#include "ptx.cuh"
 
-int srb_wgrad_umma_ok(const srb_wgrad_desc*) { return 0; }
+namespace {
 
-int srb_wgrad_umma(srb_ctx*, const srb_wgrad_desc*, const void*, const void*, float*, float*, cudaStream_t) {
-  srb_set_error("srb_conv_wgrad(umma): not available in this build");
-  return 5;
+constexpr int kThreads = 192;       // warp 0 TMA, warp 1 MMA + TMEM, warps 2-5 epilogue
+constexpr int kStages = 3;
+constexpr int kTW = 8, kTH = 16;    // 128-pixel tile, 8 wide (one swizzle atom per tile row)
+constexpr int kABytes = (kTH + 2) * kTW * 128;   // one kw-shifted input window (18 rows)
+constexpr int kGBytes = kTH * kTW * 128;         // gradient tile
+constexpr int kStageBytes = 3 * kABytes + kGBytes;
+constexpr int kMaxBlocks = 74;      // blocks per launch (kernel-parameter space: 74 x 320 B < 32 KB)
+constexpr uint32_t kTmemCols = 512; // 5 accumulators x 64 columns -> next power of two
+
+struct alignas(64) WgradBlock {
+  CUtensorMap tmX;      // x  [N,H,W,Cs] bf16, box (64, 8, 18, 1)
+  CUtensorMap tmG;      // gy [N,H,W,Cs] bf16, box (64, 8, 16, 1)
+  float* dw;            // OIHW fp32 base of the layer
+  int xc0, gc0;         // channel coordinate (offset + chunk * 64) in x / gy
+  int ci0, co0;         // first input / output channel of this block in dW (co0 in gy order)
+  int Cin, Cout;        // layer sizes (dW strides, shuffle mapping)
+  int tiles_w, tiles_h, ntiles;
+  int shuffle;
+  int rmw;              // 1: dw += (non-atomic, S == 1 and accumulate)
+  float alpha;
+};
+
+struct WgradParams {
+  WgradBlock blk[kMaxBlocks];
+  int nblocks;
+  int S;                // CTAs per block (split over tiles)
+};
+
+__global__ void __launch_bounds__(kThreads, 1) wgrad_umma_kernel(const __grid_constant__ WgradParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kStages];
+  __shared__ uint64_t empty_bar[kStages];
+  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bi = blockIdx.x / P.S, split = blockIdx.x % P.S;
+  const WgradBlock& B = P.blk[bi];
+  const uint32_t ring = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  // tiles of this CTA: split, split + S, ...
+  const int my_tiles = (B.ntiles - split + P.S - 1) / P.S;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(&tmem_full_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_acc = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && my_tiles > 0) {
+      ptx::prefetch_tensormap(&B.tmX);
+      ptx::prefetch_tensormap(&B.tmG);
+      for (int it = 0; it < my_tiles; ++it) {
+        const int t = split + it * P.S;
+        const int tw_i = t % B.tiles_w, th_i = (t / B.tiles_w) % B.tiles_h, n = t / (B.tiles_w * B.tiles_h);
+        const int h0 = th_i * kTH, w0 = tw_i * kTW;
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
+        ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)kStageBytes);
+        const uint32_t base = ring + (uint32_t)s * kStageBytes;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+          ptx::tma_load_4d(base + kw * kABytes, &B.tmX, &full_bar[s], B.xc0, w0 + kw - 1, h0 - 1, n);
+        ptx::tma_load_4d(base + 3 * kABytes, &B.tmG, &full_bar[s], B.gc0, w0, h0, n);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && my_tiles > 0) {
+      // A and B both MN-major (bits 15, 16), M = 128, N = 64
+      constexpr uint32_t idesc = ptx::idesc_bf16_f32(128, 64, 1, 1);
+      for (int it = 0; it < my_tiles; ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        ptx::mbar_wait(&full_bar[s], ph);
+        ptx::tc_fence_after();
+        const uint32_t base = ring + (uint32_t)s * kStageBytes;
+        const uint32_t gbase = base + 3 * kABytes;
+#pragma unroll 1
+        for (int a = 0; a < 5; ++a) {
+          // accumulator a: two taps stacked along M.  a<3: (kh0,kw=a)+(kh1,kw=a), second atom one
+          // tile row (1024 B) further; a=3: (kh2,kw0)+(kh2,kw1), second atom in the next window;
+          // a=4: (kh2,kw2) + don't-care rows (upper 64 lanes are discarded by the epilogue)
+          uint32_t a0, lbo;
+          if (a < 3) { a0 = base + a * kABytes; lbo = 1024u; }
+          else if (a == 3) { a0 = base + 2 * kTW * 128; lbo = (uint32_t)kABytes; }
+          else { a0 = base + 2 * kABytes + 2 * kTW * 128; lbo = 1024u; }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {   // 8 x 16 pixels
+            const uint64_t adesc = ptx::smem_desc_sw128(a0 + j * 2048u, lbo, 1024u);
+            const uint64_t bdesc = ptx::smem_desc_sw128(gbase + j * 2048u, 1024u, 1024u);
+            ptx::umma_bf16(tmem_acc + (uint32_t)a * 64u, adesc, bdesc, idesc, (uint32_t)((it | j) != 0));
+          }
+        }
+        ptx::umma_commit(&empty_bar[s]);
+      }
+      ptx::umma_commit(&tmem_full_bar);
+    }
+  } else if (my_tiles > 0) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;            // TMEM lane = (tap-in-pair, ci)
+    const int half = row >> 6, ci = B.ci0 + (row & 63);
+    const int rr = B.shuffle > 1 ? B.shuffle * B.shuffle : 1;
+    const int Cp = B.Cout / rr;
+    ptx::mbar_wait(&tmem_full_bar, 0);
+    ptx::tc_fence_after();
+#pragma unroll 1
+    for (int a = 0; a < 5; ++a) {
+      int kh, kw;
+      if (a < 3) { kh = half; kw = a; }
+      else if (a == 3) { kh = 2; kw = half; }
+      else { kh = 2; kw = 2; }
+      const bool live = !(a == 4 && half == 1);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t acc[32];
+        ptx::tmem_ld_32x32b_x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 64 + c0), acc);
+        ptx::tmem_ld_wait();
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int cop = B.co0 + c0 + j;                      // channel in gy's order
+            const int co = rr > 1 ? (cop % Cp) * rr + cop / Cp : cop;
+            float* dst = B.dw + (((int64_t)co * B.Cin + ci) * 3 + kh) * 3 + kw;
+            const float v = __uint_as_float(acc[j]) * B.alpha;
+            if (P.S > 1) atomicAdd(dst, v);       // split reduction (dW pre-zeroed or accumulated)
+            else if (B.rmw) *dst += v;            // whole reduction here, gradient accumulation
+            else *dst = v;
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_acc, kTmemCols);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_act_map(srb_ctx* ctx, CUtensorMap* map, const void* base, int N, int H, int W, int cs, int cextent,
+                   int box_h) {
+  cuuint64_t dims[4] = {(cuuint64_t)cextent, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)cs * 2, (cuuint64_t)W * cs * 2, (cuuint64_t)H * W * cs * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)kTW, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled);
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    srb_set_error("cuTensorMapEncodeTiled(wgrad) failed with CUresult %d", (int)r);
+    return 4;
+  }
+  return 0;
+}
+
+}  // namespace
+
+int srb_wgrad_umma_ok(const srb_wgrad_desc* d) {
+  if (d->dtype != SRB_BF16 || d->ksize != 3) return 0;
+  if (d->Cin % 64 || d->Cout % 64 || d->Cin < 64 || d->Cout < 64) return 0;
+  if (d->x_cs % 8 || d->x_co % 8 || d->g_cs % 8 || d->g_co % 8) return 0;
+  if (d->W < 8) return 0;
+  if (d->shuffle > 1 && (d->Cout % (d->shuffle * d->shuffle))) return 0;
+  return 1;
+}
+
+// Launches the batched kernel for a list of eligible items (all checked by the caller).
+int srb_wgrad_umma_batched(srb_ctx* ctx, const srb_wgrad_desc* descs, const void* const* xs, const void* const* gys,
+                           float* const* dws, int n_items, cudaStream_t st) {
+  static bool attr_set = false;
+  const size_t smem = (size_t)kStages * kStageBytes + 1024;
+  if (!attr_set) {
+    SRB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  std::vector<WgradBlock> blocks;
+  int min_tiles = 1 << 30;
+  for (int i = 0; i < n_items; ++i) {
+    const srb_wgrad_desc& d = descs[i];
+    CUtensorMap tmX, tmG;  // one pair per layer; its 64x64 blocks differ by channel coordinates only
+    int rc = encode_act_map(ctx, &tmX, xs[i], d.N, d.H, d.W, d.x_cs, d.x_co + d.Cin, kTH + 2);
+    if (rc) return rc;
+    rc = encode_act_map(ctx, &tmG, gys[i], d.N, d.H, d.W, d.g_cs, d.g_co + d.Cout, kTH);
+    if (rc) return rc;
+    const int tiles_w = srb_cdiv(d.W, kTW), tiles_h = srb_cdiv(d.H, kTH);
+    for (int cb = 0; cb < d.Cin / 64; ++cb) {
+      for (int ob = 0; ob < d.Cout / 64; ++ob) {
+        WgradBlock B;
+        B.tmX = tmX;
+        B.tmG = tmG;
+        B.dw = dws[i];
+        B.xc0 = d.x_co + cb * 64;
+        B.gc0 = d.g_co + ob * 64;
+        B.ci0 = cb * 64;
+        B.co0 = ob * 64;
+        B.Cin = d.Cin;
+        B.Cout = d.Cout;
+        B.tiles_w = tiles_w;
+        B.tiles_h = tiles_h;
+        B.ntiles = d.N * tiles_w * tiles_h;
+        B.shuffle = d.shuffle;
+        B.rmw = d.accumulate ? 1 : 0;
+        B.alpha = d.alpha;
+        if (B.ntiles < min_tiles) min_tiles = B.ntiles;
+        blocks.push_back(B);
+      }
+    }
+  }
+  const int total = (int)blocks.size();
+  if (total == 0) return 0;
+  // CTAs per block: fill the SMs, but keep several tiles per CTA (the epilogue costs ~40k global
+  // updates per CTA whatever its share of the reduction)
+  const int per_launch = total < kMaxBlocks ? total : kMaxBlocks;
+  int S = ctx->num_sms / per_launch;
+  if (S > 16) S = 16;
+  if (S > min_tiles) S = min_tiles;
+  if (S < 1) S = 1;
+  if (S > 1) {
+    // split reduction: CTAs add into dW with red.global.add, so overwritten layers start from zero
+    for (int i = 0; i < n_items; ++i)
+      if (!descs[i].accumulate)
+        SRB_CHECK_CUDA(cudaMemsetAsync(dws[i], 0, sizeof(float) * (size_t)descs[i].Cout * descs[i].Cin * 9, st));
+  }
+  WgradParams* P = new WgradParams();
+  int rc = 0;
+  for (int b0 = 0; b0 < total && rc == 0; b0 += kMaxBlocks) {
+    const int nb = total - b0 < kMaxBlocks ? total - b0 : kMaxBlocks;
+    for (int b = 0; b < nb; ++b) P->blk[b] = blocks[b0 + b];
+    P->nblocks = nb;
+    P->S = S;
+    wgrad_umma_kernel<<<nb * S, kThreads, smem, st>>>(*P);
+    __atomic_fetch_add(&g_srb_launches, 1ull, __ATOMIC_RELAXED);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      srb_set_error("wgrad_umma_kernel launch failed: %s", cudaGetErrorString(e));
+      rc = 1;
+    }
+  }
+  delete P;
+  return rc;
+}
+
+int srb_colsum_launch(srb_ctx* ctx, const void* x, int cs, int co, int C, int64_t npix, int dtype, float* out,
+                      int accumulate, float alpha, int shuffle, cudaStream_t st);
+
+int srb_wgrad_umma(srb_ctx* ctx, const srb_wgrad_desc* d, const void* x, const void* gy, float* dw, float* dbias,
+                   cudaStream_t st) {
+  SRB_REQUIRE(srb_wgrad_umma_ok(d), "srb_conv_wgrad(umma): not eligible (bf16, k=3, Cin,Cout %% 64 == 0, W >= 8)");
+  int rc = srb_wgrad_umma_batched(ctx, d, &x, &gy, &dw, 1, st);
+  if (rc) return rc;
+  if (dbias)  // bias gradient = per-channel sums of gy (gy's channel order -> parameter order)
+    return srb_colsum_launch(ctx, gy, d->g_cs, d->g_co, d->Cout, (int64_t)d->N * d->H * d->W, d->dtype, dbias,
+                             d->accumulate, d->alpha, d->shuffle, st);
+  return 0;
 }

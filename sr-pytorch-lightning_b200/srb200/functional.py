@@ -157,7 +157,7 @@ class RCABFn(Function):
         y1 = torch.empty_like(x)
         ops.conv(x, 0, c, p1, w1, b1.detach(), y1, 0, c, 3, relu=True)
         t = torch.empty_like(x)
-        pool = torch.zeros((n, c), dtype=torch.float32, device=x.device)
+        pool = ops.zeros_f32((n, c), x.device)
         ops.conv(y1, 0, c, p2, w2, b2.detach(), t, 0, c, 3, colsum=pool, colsum_groups=n)
         out = torch.empty_like(x)
         s = torch.empty((n, c), dtype=torch.float32, device=x.device)
@@ -178,10 +178,11 @@ class RCABFn(Function):
         cw2buf, _, dcw2 = _grad_target(cw2)
         cb2buf, _, dcb2 = _grad_target(cb2)
         b2buf, bacc2, db2 = _grad_target(b2)
-        scratch = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        scratch = ops.zeros_f32((n, c), x.device)
         if cacc != bacc2:
             raise RuntimeError("inconsistent gradient-accumulation state between CA and conv parameters")
-        ops.ca_bwd(g, t, s, yg, cw1, cb1, cw2, cb2, dt, cw1buf, cb1buf, cw2buf, cb2buf, b2buf, scratch, accumulate=cacc)
+        ops.ca_bwd(g, t, s, yg, cw1, cb1, cw2, cb2, dt, cw1buf, cb1buf, cw2buf, cb2buf, b2buf, scratch, accumulate=cacc,
+                   scratch_is_zero=True)
         w2buf, acc2, dw2 = _grad_target(w2)
         ops.conv_wgrad(y1, 0, c, dt, 0, c, 3, w2buf, None, accumulate=acc2)
         d1 = torch.empty_like(x)

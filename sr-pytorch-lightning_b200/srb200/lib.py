@@ -34,6 +34,14 @@ class WgradDesc(C.Structure):
                                      "backend", "x_cs", "x_co", "g_cs", "g_co")] + [("alpha", c_f32)]
 
 
+class PackItem(C.Structure):
+    _fields_ = [("src", c_vp), ("dst", c_vp)] + [(n, c_i32) for n in ("Cout", "Cin", "ksize", "packing", "mode", "shuffle")]
+
+
+class WgradItem(C.Structure):
+    _fields_ = [("d", WgradDesc), ("x", c_vp), ("gy", c_vp), ("dw", c_vp), ("dbias", c_vp)]
+
+
 # name -> (restype, argtypes); every symbol include/srb200.h declares
 PROTOTYPES = {
     "srb_abi_version": (c_i32, []),
@@ -47,10 +55,12 @@ PROTOTYPES = {
     "srb_pack_bias": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "srb_conv": (c_i32, [c_vp, C.POINTER(ConvDesc)] + [c_vp] * 9),
     "srb_conv_wgrad": (c_i32, [c_vp, C.POINTER(WgradDesc)] + [c_vp] * 5),
+    "srb_conv_wgrad_batched": (c_i32, [c_vp, C.POINTER(WgradItem), c_i32, c_vp]),
     "srb_conv_uses_umma": (c_i32, [C.POINTER(ConvDesc)]),
     "srb_wgrad_uses_umma": (c_i32, [C.POINTER(WgradDesc)]),
     "srb_ca_fwd": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32] + [c_vp] * 8),
-    "srb_ca_bwd": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32] + [c_vp] * 15 + [c_i32, c_vp]),
+    "srb_ca_bwd": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32] + [c_vp] * 15 + [c_i32, c_i32, c_vp]),
+    "srb_pack_table": (c_i32, [c_vp, c_vp, c_i32, c_i64, c_vp]),
     "srb_nchw_to_nhwc": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp]),
     "srb_nhwc_to_nchw": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "srb_copy_channels": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_i64, c_i32, c_vp]),

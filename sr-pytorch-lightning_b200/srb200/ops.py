@@ -10,6 +10,7 @@ addressed as (tensor, channel_offset, channels) — the replacement for torch.ca
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import torch
 
@@ -74,34 +75,136 @@ def invalidate_packed():
     _generation += 1
 
 
+_all_packs = weakref.WeakSet()
+_managed = False   # True: a PackTable re-packs every cached entry once per step; caches never go stale
+
+
 class PackedWeights:
     """Cache of packed copies of one conv weight, rebuilt when the parameter changes
     (keyed on data_ptr and the tensor version counter, SURVEY §8b "Ownership")."""
 
     def __init__(self):
         self._cache = {}
+        _all_packs.add(self)
 
     def get(self, w: torch.Tensor, packing: int, mode: int, shuffle: int = 0):
         key = (packing, mode, shuffle)
-        tag = (w.data_ptr(), w._version, w.device, _generation)
         hit = self._cache.get(key)
+        if hit is not None and _managed and hit[2].data_ptr() == w.data_ptr():
+            return hit[1]
+        tag = (w.data_ptr(), w._version, w.device, _generation)
         if hit is not None and hit[0] == tag:
             return hit[1]
         packed = pack_weight(w.detach(), packing, mode, shuffle)
-        self._cache[key] = (tag, packed)
+        self._cache[key] = (tag, packed, w.detach())
         return packed
 
     def get_bias(self, b: torch.Tensor, shuffle: int):
         if b is None or shuffle <= 1:
             return b.detach() if b is not None else None
         key = ("bias", shuffle)
-        tag = (b.data_ptr(), b._version, b.device, _generation)
         hit = self._cache.get(key)
+        if hit is not None and _managed and hit[2].data_ptr() == b.data_ptr():
+            return hit[1]
+        tag = (b.data_ptr(), b._version, b.device, _generation)
         if hit is not None and hit[0] == tag:
             return hit[1]
         packed = pack_bias(b.detach(), shuffle)
-        self._cache[key] = (tag, packed)
+        self._cache[key] = (tag, packed, b.detach())
         return packed
+
+
+class PackTable:
+    """Device table of every (parameter -> packed buffer) pair currently cached by the model's
+    PackedWeights objects; `run()` re-packs them all in one launch (srb_pack_table).  Built after
+    a warm-up step, when every conv has been through forward and backward once.  While a table is
+    installed (`_managed`), cached buffers are trusted: addresses are stable and the table refreshes
+    their contents each step."""
+
+    def __init__(self, device):
+        import numpy as np
+        rows = []
+        self.keep = []
+        max_elems = 1
+        for pw in list(_all_packs):
+            for key, (tag, packed, src) in pw._cache.items():
+                if src.device != device:
+                    continue
+                if key[0] == "bias":
+                    rows.append((src.data_ptr(), packed.data_ptr(), src.numel(), 1, 0, 0, 0, key[1]))
+                else:
+                    packing, mode, shuffle = key
+                    cout, cin, k, _ = src.shape
+                    rows.append((src.data_ptr(), packed.data_ptr(), cout, cin, k, packing, mode, shuffle))
+                    max_elems = max(max_elems, src.numel())
+                self.keep.append((packed, src))
+        dt = np.dtype([("src", "<u8"), ("dst", "<u8"), ("Cout", "<i4"), ("Cin", "<i4"), ("ksize", "<i4"),
+                       ("packing", "<i4"), ("mode", "<i4"), ("shuffle", "<i4")])
+        assert dt.itemsize == C.sizeof(L.PackItem)
+        arr = np.array(rows, dtype=dt)
+        self.n = len(rows)
+        self.max_elems = max_elems
+        self.table = torch.from_numpy(arr.view(np.uint8).copy()).to(device)
+        self.device = device
+
+    def install(self):
+        global _managed
+        _managed = True
+
+    @staticmethod
+    def uninstall():
+        global _managed
+        _managed = False
+
+    def run(self):
+        L.check(L.load().srb_pack_table(C.c_void_p(L.ctx(self.device.index)), _p(self.table), self.n, self.max_elems,
+                                        _stream()), "srb_pack_table")
+
+
+class ZeroArena:
+    """One fp32 buffer cleared once per step; kernels that accumulate with atomics (pooled sums,
+    CA scratch) take zero-initialised slices from it instead of launching a fill each."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buf = None
+        self.off = 0
+        self.need = 0
+
+    def reset(self):
+        if self.buf is None or self.buf.numel() < self.need:
+            self.buf = torch.zeros(max(self.need, 1024), dtype=torch.float32, device=self.device)
+        else:
+            self.buf.zero_()
+        self.off = 0
+        self.need = 0
+
+    def take(self, shape):
+        n = 1
+        for s in shape:
+            n *= int(s)
+        n4 = (n + 3) // 4 * 4
+        self.need += n4
+        if self.buf is None or self.off + n4 > self.buf.numel():
+            return torch.zeros(shape, dtype=torch.float32, device=self.device)   # sizing pass
+        out = self.buf[self.off:self.off + n].view(shape)
+        self.off += n4
+        return out
+
+
+_arena = None
+
+
+def set_arena(arena):
+    global _arena
+    _arena = arena
+
+
+def zeros_f32(shape, device):
+    """Zero-initialised fp32 scratch: a slice of the per-step arena when one is active."""
+    if _arena is not None and _arena.device == device:
+        return _arena.take(shape)
+    return torch.zeros(shape, dtype=torch.float32, device=device)
 
 
 # --------------------------------------------------------------------------------------------
@@ -173,6 +276,60 @@ def conv_dgrad_shuffled(gu, weights: PackedWeights, w_param, y, shuffle, **kw):
     return y
 
 
+class _WgradQueue:
+    """Deferred weight gradients.  Inside `deferred_wgrads()` every conv_wgrad call is recorded
+    (tensors kept alive) instead of launched; the flush hands the whole list to
+    srb_conv_wgrad_batched, where the tcgen05-eligible layers share a few persistent launches."""
+
+    def __init__(self):
+        self.active = False
+        self.items = []
+        self.max_items = 296
+
+    def push(self, desc, x, gy, dw, dbias):
+        self.items.append((desc, x, gy, dw, dbias))
+        if len(self.items) >= self.max_items:
+            self.flush()
+
+    def flush(self):
+        if not self.items:
+            return
+        items, self.items = self.items, []
+        arr = (L.WgradItem * len(items))()
+        for i, (d, x, gy, dw, dbias) in enumerate(items):
+            arr[i].d = d
+            arr[i].x = x.data_ptr()
+            arr[i].gy = gy.data_ptr()
+            arr[i].dw = dw.data_ptr()
+            arr[i].dbias = dbias.data_ptr() if dbias is not None else None
+        L.check(L.load().srb_conv_wgrad_batched(_ctx(items[0][1]), arr, len(items), _stream()), "srb_conv_wgrad_batched")
+
+
+_wq = _WgradQueue()
+
+
+class deferred_wgrads:
+    """Context manager: defer and batch the weight-gradient launches issued inside (used around
+    `loss.backward()` by srb200.trainer).  All launches happen on the current stream at exit, so
+    gradients are complete before anything enqueued later on that stream reads them."""
+
+    def __init__(self, max_items: int = 296):
+        self.max_items = max_items
+
+    def __enter__(self):
+        _wq.active = True
+        _wq.max_items = self.max_items
+        return _wq
+
+    def __exit__(self, *exc):
+        _wq.active = False
+        if exc[0] is None:
+            _wq.flush()
+        else:
+            _wq.items = []
+        return False
+
+
 def conv_wgrad(x, x_co, cin, gy, g_co, cout, k, dw, dbias, *, accumulate=False, shuffle=0, alpha=1.0,
                backend=L.BACKEND_AUTO):
     """dw (fp32 OIHW) (+)= alpha * correlation(x, gy); dbias (+)= alpha * sum(gy)."""
@@ -188,6 +345,9 @@ def conv_wgrad(x, x_co, cin, gy, g_co, cout, k, dw, dbias, *, accumulate=False, 
     d.x_cs, d.x_co = xcs, x_co
     d.g_cs, d.g_co = gy.shape[3], g_co
     d.alpha = float(alpha)
+    if _wq.active:
+        _wq.push(d, x, gy, dw, dbias)
+        return
     L.check(lib.srb_conv_wgrad(_ctx(x), C.byref(d), _p(x), _p(gy), _p(dw), _p(dbias), _stream()), "srb_conv_wgrad")
 
 
@@ -202,12 +362,13 @@ def ca_fwd(t, skip, pooled_sum, compute_pool, w1, b1, w2, b2, out, s_out, y_out)
                                 _stream()), "srb_ca_fwd")
 
 
-def ca_bwd(g, t, s, y, w1, b1, w2, b2, dt, dw1, db1, dw2, db2, colsum_dt, scratch, accumulate=False):
+def ca_bwd(g, t, s, y, w1, b1, w2, b2, dt, dw1, db1, dw2, db2, colsum_dt, scratch, accumulate=False,
+           scratch_is_zero=False):
     n, h, w, c = _nhwc(t)
     cr = w1.shape[0]
     L.check(L.load().srb_ca_bwd(_ctx(t), n, h, w, c, cr, dtype_code(t), _p(g), _p(t), _p(s), _p(y), _p(w1), _p(b1),
                                 _p(w2), _p(b2), _p(dt), _p(dw1), _p(db1), _p(dw2), _p(db2), _p(colsum_dt), _p(scratch),
-                                1 if accumulate else 0, _stream()), "srb_ca_bwd")
+                                1 if scratch_is_zero else 0, 1 if accumulate else 0, _stream()), "srb_ca_bwd")
 
 
 # --------------------------------------------------------------------------------------------

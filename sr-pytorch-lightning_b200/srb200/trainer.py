@@ -7,6 +7,10 @@ What it replaces in the reference: Lightning's fit loop around `SRModel.training
 defaults) and the implicit DDP gradient all-reduce (SURVEY §2.1).  Python runs once, at capture;
 a replayed step is a single `cudaGraphLaunch` — the >5000 eager launches per RCAN step the
 reference issues never touch the host again.
+
+Per step, outside the conv/CA kernels themselves, the graph holds: one table-driven re-pack of all
+weights (srb_pack_table), one memset of the flat gradient buffer, one memset of the zero arena
+(pooled sums / CA scratch), a handful of batched weight-gradient launches, one Adam launch.
 """
 from __future__ import annotations
 
@@ -47,10 +51,13 @@ class FlatParams:
                 p._srb_grad_live = False
         self.offsets = offs
 
-    def begin_step(self):
-        """First gradient write of a step overwrites, later ones accumulate: no zero-fill pass."""
+    def begin_step(self, zero: bool = True):
+        """zero=True: clear the whole gradient buffer with one memset and let every kernel
+        accumulate (no per-layer fills).  zero=False: the first write of each gradient overwrites."""
+        if zero:
+            self.grad.zero_()
         for p in self.params:
-            p._srb_grad_live = False
+            p._srb_grad_live = zero
 
     def grads_by_name(self, model):
         return {k: p._srb_grad for k, p in model.named_parameters() if p.requires_grad}
@@ -73,6 +80,7 @@ class TrainStep:
         self.model = model
         self.flat = FlatParams(model)
         dev = self.flat.flat.device
+        self.device = dev
         n, c, h, w = lr_shape
         self.x = torch.zeros(lr_shape, dtype=torch.float32, device=dev)
         self.hr = torch.zeros((n, c, h * scale, w * scale), dtype=torch.float32, device=dev)
@@ -83,38 +91,56 @@ class TrainStep:
         self.use_graph = use_graph
         self.graph = None
         self.launches_per_step = 0
+        self.arena = ops.ZeroArena(dev)
+        self.pack_table = None
 
     # the work of one step; captured once
     def _body(self):
-        self.flat.begin_step()
-        ops.invalidate_packed()                       # weights changed: re-pack inside the step
-        sr = self.model.forward(self.x)
-        loss = F200.l1_loss(sr, self.hr)
-        loss.backward()
-        if self.world > 1:
-            dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.pg)
-        ops.inc_counter(self.flat.step_dev)
-        ops.adam_step(self.flat.flat, self.flat.grad, self.flat.m, self.flat.v, step=0, step_dev=self.flat.step_dev,
-                      grad_scale=1.0 / self.world, **self.hp)
-        self.loss.copy_(loss.detach())
+        ops.set_arena(self.arena)
+        try:
+            self.arena.reset()
+            self.flat.begin_step(zero=True)
+            if self.pack_table is not None:
+                self.pack_table.run()                 # all packed weight copies, one launch
+            else:
+                ops.invalidate_packed()               # (warm-up) re-pack lazily, conv by conv
+            sr = self.model.forward(self.x)
+            loss = F200.l1_loss(sr, self.hr)
+            with ops.deferred_wgrads():               # weight gradients batched, off the dgrad chain
+                loss.backward()
+            if self.world > 1:
+                dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.pg)
+            ops.inc_counter(self.flat.step_dev)
+            ops.adam_step(self.flat.flat, self.flat.grad, self.flat.m, self.flat.v, step=0,
+                          step_dev=self.flat.step_dev, grad_scale=1.0 / self.world, **self.hp)
+            self.loss.copy_(loss.detach())
+        finally:
+            ops.set_arena(None)
 
-    def capture(self, warmup: int = 2):
+    def prepare(self, warmup: int = 2):
+        """Warm-up steps (sizes the arena, fills the packed-weight caches), then build the pack
+        table and, if enabled, capture the step into a CUDA graph."""
         from . import lib as L
-        if not self.use_graph:
-            return
-        side = torch.cuda.Stream()
+        side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(warmup):
+            for _ in range(max(2, warmup)):
                 self._body()
+            self.pack_table = ops.PackTable(self.device)
+            self.pack_table.install()
+            self._body()                              # one more eager step through the table path
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        if not self.use_graph:
+            return
         c0 = L.launch_count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._body()
         self.launches_per_step = L.launch_count() - c0
         torch.cuda.synchronize()
+
+    capture = prepare
 
     def load_batch(self, lr_batch, hr_batch):
         self.x.copy_(lr_batch, non_blocking=True)
@@ -133,3 +159,7 @@ class TrainStep:
     def step(self, lr_batch, hr_batch):
         self.load_batch(lr_batch, hr_batch)
         return self.run()
+
+    def close(self):
+        ops.PackTable.uninstall()
+        self.flat.detach()

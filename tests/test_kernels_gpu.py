@@ -357,3 +357,83 @@ def test_errors_are_reported_not_thrown():
         ops.conv(x, 0, 48, ops.PackedWeights(), w3, None, y, 0, 64, 3, backend=L.BACKEND_UMMA)
     with pytest.raises(RuntimeError, match="CUDA tensors"):
         ops.nchw_to_nhwc(torch.zeros(1, 3, 4, 4), None, torch.float32)
+
+
+WGRAD_UMMA_CASES = [
+    dict(n=1, h=16, w=8, cin=64, cout=64),                         # one tile
+    dict(n=2, h=48, w=48, cin=64, cout=64),                        # the hot RCAN/EDSR shape
+    dict(n=1, h=20, w=13, cin=64, cout=64),                        # ragged tiles
+    dict(n=1, h=16, w=16, cin=128, cout=192),                      # several 64x64 blocks per layer
+    dict(n=1, h=16, w=16, cin=64, cout=256, shuffle=2),            # un-shuffled gradient channel order
+    dict(n=2, h=16, w=16, cin=64, cout=64, alpha=0.1, accumulate=True),
+    dict(n=1, h=16, w=16, cin=64, cout=64, x_cs=192, x_co=64, g_cs=128, g_co=64),   # channel slices
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_UMMA_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_conv_wgrad_umma(case):
+    """tcgen05 weight gradient (MN-major operands, taps stacked along M) vs autograd in fp64 on
+    the same bf16-rounded operands; bias gradient through the fused column-sum launch."""
+    from srb200 import lib as L, ops
+    c = dict(case)
+    n, h, w, cin, cout = c["n"], c["h"], c["w"], c["cin"], c["cout"]
+    shuffle, alpha, accumulate = c.get("shuffle", 0), c.get("alpha", 1.0), c.get("accumulate", False)
+    x_cs, x_co = c.get("x_cs", cin), c.get("x_co", 0)
+    g_cs, g_co = c.get("g_cs", cout), c.get("g_co", 0)
+    g = torch.Generator().manual_seed(6)
+    xfull = torch.randn(n, h, w, x_cs, generator=g).to(torch.bfloat16)
+    r = shuffle if shuffle else 1
+    gy = torch.randn(n, h * r, w * r, cout // (r * r), generator=g).to(torch.bfloat16)
+    wt = torch.zeros(cout, cin, 3, 3, dtype=torch.float64, requires_grad=True)
+    bt = torch.zeros(cout, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(_nchw(xfull[..., x_co:x_co + cin].double()), wt, bt, padding=1)
+    if shuffle:
+        y = F.pixel_shuffle(y, r)
+    y.backward(_nchw(gy.double()))
+    dev = _dev()
+    base = torch.randn(cout, cin, 3, 3, generator=g)
+    dw = base.to(dev).clone() if accumulate else torch.full((cout, cin, 3, 3), 3.0, device=dev)
+    db = torch.zeros(cout, device=dev) if accumulate else torch.full((cout,), 3.0, device=dev)
+    gyd = gy.to(dev)
+    if shuffle:
+        gyd = ops.pixel_unshuffle(gyd, r)
+    if g_cs != cout:
+        gfull = torch.randn(n, h, w, g_cs, generator=g).to(torch.bfloat16).to(dev)
+        gfull[..., g_co:g_co + cout] = gyd
+        gyd = gfull
+    ops.conv_wgrad(xfull.to(dev), x_co, cin, gyd, g_co, cout, 3, dw, db, accumulate=accumulate, shuffle=shuffle,
+                   alpha=alpha, backend=L.BACKEND_UMMA)
+    torch.cuda.synchronize()
+    want_w = wt.grad * alpha + (base.double() if accumulate else 0)
+    l2w, mxw = _rel(dw, want_w)
+    l2b, _ = _rel(db, bt.grad * alpha)
+    assert l2w < 2e-5 and l2b < 2e-5, (l2w, mxw, l2b)
+
+
+def test_conv_wgrad_batched_deferred():
+    """Several layers through ops.deferred_wgrads(): one srb_conv_wgrad_batched call, results equal
+    to the one-by-one launches (tcgen05-eligible and CUDA-core layers mixed)."""
+    from srb200 import ops
+    g = torch.Generator().manual_seed(7)
+    dev = _dev()
+    layers = []
+    for i, (cin, cout, hw) in enumerate([(64, 64, 48), (64, 64, 48), (3, 64, 24), (64, 128, 16), (64, 3, 32), (64, 64, 48)]):
+        x = torch.randn(2, hw, hw, cin, generator=g).to(torch.bfloat16).to(dev)
+        gy = torch.randn(2, hw, hw, cout, generator=g).to(torch.bfloat16).to(dev)
+        layers.append((x, gy, cin, cout))
+    ref = []
+    for x, gy, cin, cout in layers:
+        dw = torch.empty(cout, cin, 3, 3, device=dev)
+        db = torch.empty(cout, device=dev)
+        ops.conv_wgrad(x, 0, cin, gy, 0, cout, 3, dw, db)
+        ref.append((dw, db))
+    got = []
+    with ops.deferred_wgrads():
+        for x, gy, cin, cout in layers:
+            dw = torch.full((cout, cin, 3, 3), 9.0, device=dev)
+            db = torch.full((cout,), 9.0, device=dev)
+            ops.conv_wgrad(x, 0, cin, gy, 0, cout, 3, dw, db)
+            got.append((dw, db))
+    torch.cuda.synchronize()
+    for (dw, db), (rw, rb) in zip(got, ref):
+        assert _rel(dw, rw)[0] < 1e-5 and _rel(db, rb)[0] < 1e-5
