@@ -106,6 +106,21 @@ def main():
             for j in range(74):
                 ops.conv_wgrad(xs[(i + j) % NBUF], 0, 64, zs[(i + j) % NBUF], 0, 64, 3, dws74[j], None, accumulate=True)
     out["wgrad3x3_64_batched_per_layer"] = timed(wg_batch, reps=6) / 74
+    # tail-shaped layers (192x192, 64 <-> 3 channels) and the pixel-unshuffle
+    xt = [torch.randn(N, 192, 192, 64, device=dev).to(bf) for _ in range(4)]
+    y3 = [torch.empty(N, 192, 192, 8, device=dev, dtype=bf) for _ in range(4)]
+    g3 = [torch.randn(N, 192, 192, 8, device=dev).to(bf) for _ in range(4)]
+    wt = torch.randn(3, 64, 3, 3, device=dev) * 0.04
+    bt = torch.zeros(3, device=dev)
+    pk = ops.PackedWeights()
+    out["tail_conv_64to3_fwd"] = timed(lambda i: ops.conv(xt[i % 4], 0, 64, pk, wt, bt, y3[i % 4], 0, 3, 3), reps=16)
+    out["tail_conv_dgrad_3to64"] = timed(lambda i: ops.conv(g3[i % 4], 0, 3, pk, wt, None, xt[(i + 1) % 4], 0, 64, 3,
+                                                          mode=L.PACK_DGRAD), reps=16)
+    dwt = torch.zeros(3, 64, 3, 3, device=dev)
+    dbt = torch.zeros(3, device=dev)
+    out["tail_conv_wgrad"] = timed(lambda i: ops.conv_wgrad(xt[i % 4], 0, 64, g3[i % 4], 0, 3, 3, dwt, dbt, accumulate=True), reps=8)
+    gs = [torch.randn(N, 192, 192, 64, device=dev).to(bf) for _ in range(2)]
+    out["pixel_unshuffle_192"] = timed(lambda i: ops.pixel_unshuffle(gs[i % 2], 2), reps=8)
     for k, v in out.items():
         print(f"{k:36s} {v:9.2f} us   {flop / (v * 1e-6) / 1e12 if 'ca_' not in k else 0:8.1f} TFLOP/s")
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

@@ -4,40 +4,70 @@
 // round-trips through global memory between a "gate" and a "scale" launch.
 //
 // forward :  s = mean_hw(t); z = relu(W1 s + b1); y = sigmoid(W2 z + b2); out = t*y + skip
-// backward:  dy = sum_hw(g*t); du = dy*y*(1-y); dz = W2^T du; dv = dz*[v>0]; ds = W1^T dv
+// backward:  dy = sum_hw(g*t); du = dy*sigmoid'(u); dz = W2^T du; dv = dz*[v>0]; ds = W1^T dv
 //            dt = g*y + ds/HW ;  dW2 += du z^T, db2 += du, dW1 += dv s^T, db1 += dv
+//
+// Streaming layout: a thread owns one 16-byte vector of channels (8 bf16 / 4 fp32) of a pixel;
+// every thread first ISSUES the loads of its pixels (up to kPix per thread stay in registers) and
+// only then runs the gate MLP, so the dependent-latency chain of the gate (pooled sums -> FC ->
+// ReLU -> FC -> sigmoid, ~2 us) overlaps the memory latency instead of preceding it.
 #include "common.cuh"
 
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+constexpr int kPix = 4;  // pixels kept in flight per thread
+
 // sums over H*W per (n, c):  out[n][c] += sum  (out pre-zeroed).  MUL: sum of a*b instead of a.
 template <typename T, bool MUL>
-__global__ void ca_reduce_kernel(const T* __restrict__ a, const T* __restrict__ b, int HW, int C,
-                                 float* __restrict__ out) {
-  extern __shared__ double red[];  // [C]; cross-thread sums in fp64 (the per-thread partials are short)
-  const int cg = C / 4;
+__global__ void __launch_bounds__(256) ca_reduce_kernel(const T* __restrict__ a, const T* __restrict__ b, int HW, int C,
+                                                        float* __restrict__ out) {
+  using V = VecT<T>;
+  extern __shared__ float red_s[];  // [lanes][C]
+  const int cg = C / V::W;
   const int n = blockIdx.y;
   const int g = threadIdx.x % cg, lane = threadIdx.x / cg, lanes = blockDim.x / cg;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) red[i] = 0.0;
-  __syncthreads();
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float acc[V::W];
+#pragma unroll
+  for (int j = 0; j < V::W; ++j) acc[j] = 0.f;
   if (lane < lanes) {
-    for (int p = blockIdx.x * lanes + lane; p < HW; p += gridDim.x * lanes) {
-      int64_t off = ((int64_t)n * HW + p) * C + g * 4;
-      float4 v = ld4(a + off);
-      if (MUL) {
-        float4 u = ld4(b + off);
-        v.x *= u.x; v.y *= u.y; v.z *= u.z; v.w *= u.w;
+    const int stride = gridDim.x * lanes;
+    for (int p0 = blockIdx.x * lanes + lane; p0 < HW; p0 += stride * kPix) {
+      typename V::raw ra[kPix], rb[kPix];
+#pragma unroll
+      for (int u = 0; u < kPix; ++u) {
+        const int p = p0 + u * stride;
+        if (p < HW) {
+          const int64_t off = ((int64_t)n * HW + p) * C + g * V::W;
+          ra[u] = *reinterpret_cast<const typename V::raw*>(a + off);
+          if (MUL) rb[u] = *reinterpret_cast<const typename V::raw*>(b + off);
+        }
       }
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+#pragma unroll
+      for (int u = 0; u < kPix; ++u) {
+        const int p = p0 + u * stride;
+        if (p < HW) {
+          float fa[V::W], fb[V::W];
+          V::unpack(ra[u], fa);
+          if (MUL) {
+            V::unpack(rb[u], fb);
+#pragma unroll
+            for (int j = 0; j < V::W; ++j) acc[j] = fmaf(fa[j], fb[j], acc[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < V::W; ++j) acc[j] += fa[j];
+          }
+        }
+      }
     }
-    atomicAdd(&red[g * 4 + 0], (double)acc.x);
-    atomicAdd(&red[g * 4 + 1], (double)acc.y);
-    atomicAdd(&red[g * 4 + 2], (double)acc.z);
-    atomicAdd(&red[g * 4 + 3], (double)acc.w);
+#pragma unroll
+    for (int j = 0; j < V::W; ++j) red_s[lane * C + g * V::W + j] = acc[j];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(out + (int64_t)n * C + i, (float)red[i]);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double s = 0.0;  // cross-thread sum in fp64 (the per-thread partials are short)
+    for (int l = 0; l < lanes; ++l) s += (double)red_s[l * C + c];
+    atomicAdd(out + (int64_t)n * C + c, (float)s);
+  }
 }
 
 // gate MLP from pooled sums; every thread of the block cooperates. smem: s[C] z[Cr] y[C]
@@ -65,15 +95,37 @@ __device__ __forceinline__ void ca_gate(const float* __restrict__ sums, float in
 }
 
 template <typename T>
-__global__ void ca_scale_kernel(const T* __restrict__ t, const T* __restrict__ skip, const float* __restrict__ sums,
-                                int HW, int C, int Cr, const float* __restrict__ w1, const float* __restrict__ b1,
-                                const float* __restrict__ w2, const float* __restrict__ b2, T* __restrict__ out,
-                                float* __restrict__ s_out, float* __restrict__ y_out) {
+__global__ void __launch_bounds__(256) ca_scale_kernel(const T* __restrict__ t, const T* __restrict__ skip,
+                                                       const float* __restrict__ sums, int HW, int C, int Cr,
+                                                       const float* __restrict__ w1, const float* __restrict__ b1,
+                                                       const float* __restrict__ w2, const float* __restrict__ b2,
+                                                       T* __restrict__ out, float* __restrict__ s_out,
+                                                       float* __restrict__ y_out) {
+  using V = VecT<T>;
   extern __shared__ float sm[];
   float* s_s = sm;
   float* y_s = sm + C;
   float* z_s = sm + 2 * C;
   const int n = blockIdx.y;
+  const int cg = C / V::W;
+  const int g = threadIdx.x % cg, lane = threadIdx.x / cg, lanes = blockDim.x / cg;
+  const int stride = gridDim.x * lanes;
+  const int pfirst = blockIdx.x * lanes + lane;
+  const bool active = lane < lanes;
+  // 1) put the first batch of loads in flight
+  typename V::raw rt[kPix], rs[kPix];
+  if (active) {
+#pragma unroll
+    for (int u = 0; u < kPix; ++u) {
+      const int p = pfirst + u * stride;
+      if (p < HW) {
+        const int64_t off = ((int64_t)n * HW + p) * C + g * V::W;
+        rt[u] = *reinterpret_cast<const typename V::raw*>(t + off);
+        if (skip) rs[u] = *reinterpret_cast<const typename V::raw*>(skip + off);
+      }
+    }
+  }
+  // 2) gate (dependent chain) while they land
   ca_gate(sums + (int64_t)n * C, 1.f / (float)HW, C, Cr, w1, b1, w2, b2, s_s, z_s, y_s);
   if (blockIdx.x == 0) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -81,44 +133,76 @@ __global__ void ca_scale_kernel(const T* __restrict__ t, const T* __restrict__ s
       y_out[(int64_t)n * C + c] = y_s[c];
     }
   }
-  const int cg = C / 4;
-  const int g = threadIdx.x % cg, lane = threadIdx.x / cg, lanes = blockDim.x / cg;
-  if (lane >= lanes) return;
-  const float4 yv = make_float4(y_s[g * 4], y_s[g * 4 + 1], y_s[g * 4 + 2], y_s[g * 4 + 3]);
-  for (int p = blockIdx.x * lanes + lane; p < HW; p += gridDim.x * lanes) {
-    int64_t off = ((int64_t)n * HW + p) * C + g * 4;
-    float4 v = ld4(t + off);
-    v.x *= yv.x; v.y *= yv.y; v.z *= yv.z; v.w *= yv.w;
-    if (skip) {
-      float4 u = ld4(skip + off);
-      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+  if (!active) return;
+  float yv[V::W];
+#pragma unroll
+  for (int j = 0; j < V::W; ++j) yv[j] = y_s[g * V::W + j];
+  for (int p0 = pfirst; p0 < HW; p0 += stride * kPix) {
+    if (p0 != pfirst) {
+#pragma unroll
+      for (int u = 0; u < kPix; ++u) {
+        const int p = p0 + u * stride;
+        if (p < HW) {
+          const int64_t off = ((int64_t)n * HW + p) * C + g * V::W;
+          rt[u] = *reinterpret_cast<const typename V::raw*>(t + off);
+          if (skip) rs[u] = *reinterpret_cast<const typename V::raw*>(skip + off);
+        }
+      }
     }
-    st4(out + off, v);
+#pragma unroll
+    for (int u = 0; u < kPix; ++u) {
+      const int p = p0 + u * stride;
+      if (p < HW) {
+        float ft[V::W], fs[V::W];
+        V::unpack(rt[u], ft);
+        if (skip) {
+          V::unpack(rs[u], fs);
+#pragma unroll
+          for (int j = 0; j < V::W; ++j) ft[j] = fmaf(ft[j], yv[j], fs[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < V::W; ++j) ft[j] *= yv[j];
+        }
+        const int64_t off = ((int64_t)n * HW + p) * C + g * V::W;
+        *reinterpret_cast<typename V::raw*>(out + off) = V::pack(ft);
+      }
+    }
   }
 }
 
 template <typename T>
-__global__ void ca_bwd_apply_kernel(const T* __restrict__ g, const float* __restrict__ s, const float* __restrict__ y,
-                                    const float* __restrict__ dysum, int HW, int C, int Cr,
-                                    const float* __restrict__ w1, const float* __restrict__ b1,
-                                    const float* __restrict__ w2, const float* __restrict__ b2, T* __restrict__ dt,
-                                    float* __restrict__ dw1,
-                                    float* __restrict__ db1, float* __restrict__ dw2, float* __restrict__ db2,
-                                    float* __restrict__ colsum_dt) {
+__global__ void __launch_bounds__(256) ca_bwd_apply_kernel(
+    const T* __restrict__ g, const float* __restrict__ s, const float* __restrict__ y, const float* __restrict__ dysum,
+    int HW, int C, int Cr, const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+    const float* __restrict__ b2, T* __restrict__ dt, float* __restrict__ dw1, float* __restrict__ db1,
+    float* __restrict__ dw2, float* __restrict__ db2, float* __restrict__ colsum_dt) {
+  using V = VecT<T>;
   extern __shared__ float sm[];
   float* s_s = sm;             // [C]
   float* y_s = sm + C;         // [C]
   float* du_s = sm + 2 * C;    // [C]
   float* ds_s = sm + 3 * C;    // [C]  (already divided by HW)
-  float* cs_s = sm + 4 * C;    // [C]  column sums of dt
-  float* z_s = sm + 5 * C;     // [Cr]
+  float* z_s = sm + 4 * C;     // [Cr]
   float* dv_s = z_s + Cr;      // [Cr]
+  float* cs_s = dv_s + Cr;     // [lanes][C] column sums of dt (only if colsum_dt)
   const int n = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane_w = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int cg = C / V::W;
+  const int gi = threadIdx.x % cg, lane = threadIdx.x / cg, lanes = blockDim.x / cg;
+  const int stride = gridDim.x * lanes;
+  const int pfirst = blockIdx.x * lanes + lane;
+  const bool active = lane < lanes;
+  typename V::raw rg[kPix];
+  if (active) {
+#pragma unroll
+    for (int u = 0; u < kPix; ++u) {
+      const int p = pfirst + u * stride;
+      if (p < HW) rg[u] = *reinterpret_cast<const typename V::raw*>(g + ((int64_t)n * HW + p) * C + gi * V::W);
+    }
+  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     s_s[c] = s[(int64_t)n * C + c];
     y_s[c] = y[(int64_t)n * C + c];
-    cs_s[c] = 0.f;
   }
   __syncthreads();
   // recompute the hidden layer (needed for dW2 and the ReLU mask)
@@ -165,79 +249,112 @@ __global__ void ca_bwd_apply_kernel(const T* __restrict__ g, const float* __rest
     for (int j = threadIdx.x; j < Cr; j += blockDim.x) atomicAdd(db1 + j, dv_s[j]);
   }
   __syncthreads();
-  const int cg = C / 4;
-  const int gi = threadIdx.x % cg, lane = threadIdx.x / cg, lanes = blockDim.x / cg;
-  float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (lane < lanes) {
-    const float4 yv = make_float4(y_s[gi * 4], y_s[gi * 4 + 1], y_s[gi * 4 + 2], y_s[gi * 4 + 3]);
-    const float4 dv = make_float4(ds_s[gi * 4], ds_s[gi * 4 + 1], ds_s[gi * 4 + 2], ds_s[gi * 4 + 3]);
-    for (int p = blockIdx.x * lanes + lane; p < HW; p += gridDim.x * lanes) {
-      int64_t off = ((int64_t)n * HW + p) * C + gi * 4;
-      float4 v = ld4(g + off);
-      v.x = v.x * yv.x + dv.x; v.y = v.y * yv.y + dv.y; v.z = v.z * yv.z + dv.z; v.w = v.w * yv.w + dv.w;
-      st4(dt + off, v);
-      if (colsum_dt) {
-        float4 r = ld4(dt + off);  // sum what was stored (rounded)
-        csum.x += r.x; csum.y += r.y; csum.z += r.z; csum.w += r.w;
-      }
+  float csum[V::W];
+#pragma unroll
+  for (int j = 0; j < V::W; ++j) csum[j] = 0.f;
+  if (active) {
+    float yv[V::W], dv[V::W];
+#pragma unroll
+    for (int j = 0; j < V::W; ++j) {
+      yv[j] = y_s[gi * V::W + j];
+      dv[j] = ds_s[gi * V::W + j];
     }
-    if (colsum_dt) {
-      atomicAdd(&cs_s[gi * 4 + 0], csum.x);
-      atomicAdd(&cs_s[gi * 4 + 1], csum.y);
-      atomicAdd(&cs_s[gi * 4 + 2], csum.z);
-      atomicAdd(&cs_s[gi * 4 + 3], csum.w);
+    for (int p0 = pfirst; p0 < HW; p0 += stride * kPix) {
+      if (p0 != pfirst) {
+#pragma unroll
+        for (int u = 0; u < kPix; ++u) {
+          const int p = p0 + u * stride;
+          if (p < HW) rg[u] = *reinterpret_cast<const typename V::raw*>(g + ((int64_t)n * HW + p) * C + gi * V::W);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kPix; ++u) {
+        const int p = p0 + u * stride;
+        if (p < HW) {
+          float f[V::W];
+          V::unpack(rg[u], f);
+#pragma unroll
+          for (int j = 0; j < V::W; ++j) f[j] = fmaf(f[j], yv[j], dv[j]);
+          const typename V::raw packed = V::pack(f);
+          *reinterpret_cast<typename V::raw*>(dt + ((int64_t)n * HW + p) * C + gi * V::W) = packed;
+          if (colsum_dt) {
+            float r[V::W];
+            V::unpack(packed, r);   // sum what was stored (rounded)
+#pragma unroll
+            for (int j = 0; j < V::W; ++j) csum[j] += r[j];
+          }
+        }
+      }
     }
   }
   if (colsum_dt) {
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < V::W; ++j) cs_s[lane * C + gi * V::W + j] = csum[j];
+    }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(colsum_dt + c, cs_s[c]);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float tot = 0.f;
+      for (int l = 0; l < lanes; ++l) tot += cs_s[l * C + c];
+      atomicAdd(colsum_dt + c, tot);
+    }
   }
 }
 
-static int ca_block_threads(int C) {
-  int cg = C / 4;
-  int lanes = 256 / cg;
-  if (lanes < 1) lanes = 1;
-  int th = cg * lanes;
-  return ((th + 31) / 32) * 32;  // whole warps (extra threads idle in the streaming part)
+struct CaLaunch {
+  int threads, lanes, slabs;
+};
+
+static CaLaunch ca_launch(srb_ctx* ctx, int N, int HW, int C, int vw) {
+  CaLaunch l;
+  const int cg = C / vw;
+  l.lanes = 256 / cg;
+  if (l.lanes < 1) l.lanes = 1;
+  l.threads = ((cg * l.lanes + 31) / 32) * 32;   // whole warps (extra threads idle in the streaming part)
+  // each thread keeps kPix pixels in flight: one pass over the sample needs HW / (lanes*kPix) blocks;
+  // cap the total at ~4 blocks per SM
+  int want = srb_cdiv(HW, l.lanes * kPix);
+  int cap = (ctx->num_sms * 4 + N - 1) / N;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  l.slabs = want;
+  return l;
 }
 
-static int ca_slabs(srb_ctx* ctx, int N, int HW, int threads, int C) {
-  int lanes = threads / (C / 4);
-  if (lanes < 1) lanes = 1;
-  int want = (ctx->num_sms * 4 + N - 1) / N;           // ~4 blocks per SM over the whole batch
-  int maxs = (HW + lanes * 4 - 1) / (lanes * 4);       // at least 4 pixels per thread
-  if (want > maxs) want = maxs;
-  if (want < 1) want = 1;
-  return want;
+static int ca_check(int C, int Cr, int dtype, const char* who) {
+  const int vw = dtype == SRB_F32 ? 4 : 8;
+  SRB_REQUIRE(C % vw == 0 && C / vw <= 256 && Cr >= 1 && Cr <= 64,
+              "%s: unsupported C=%d Cr=%d", who, C, Cr);
+  return 0;
 }
 
 extern "C" int srb_ca_fwd(srb_ctx* ctx, int N, int H, int W, int C, int Cr, int dtype, const void* t, const void* skip,
                           float* pooled_sum, int compute_pool, const float* w1, const float* b1, const float* w2,
                           const float* b2, void* out, float* s_out, float* y_out, void* stream) {
   SRB_REQUIRE(ctx && t && pooled_sum && w1 && b1 && w2 && b2 && out && s_out && y_out, "srb_ca_fwd: null argument");
-  SRB_REQUIRE(C % 4 == 0 && C <= 1024 && Cr >= 1 && Cr <= 64, "srb_ca_fwd: unsupported C=%d Cr=%d", C, Cr);
+  int rc = ca_check(C, Cr, dtype, "srb_ca_fwd");
+  if (rc) return rc;
   SRB_REQUIRE(N <= 65535, "srb_ca_fwd: batch too large");
   const int HW = H * W;
-  const int threads = ca_block_threads(C);
-  const int slabs = ca_slabs(ctx, N, HW, threads, C);
-  dim3 grid(slabs, N);
+  const CaLaunch l = ca_launch(ctx, N, HW, C, dtype == SRB_F32 ? 4 : 8);
+  dim3 grid(l.slabs, N);
   if (compute_pool) {
     SRB_CHECK_CUDA(cudaMemsetAsync(pooled_sum, 0, sizeof(float) * (size_t)N * C, S(stream)));
+    const size_t rs = sizeof(float) * (size_t)l.lanes * C;
     if (dtype == SRB_F32)
-      ca_reduce_kernel<float, false><<<grid, threads, C * sizeof(double), S(stream)>>>((const float*)t, nullptr, HW, C, pooled_sum);
+      ca_reduce_kernel<float, false><<<grid, l.threads, rs, S(stream)>>>((const float*)t, nullptr, HW, C, pooled_sum);
     else
-      ca_reduce_kernel<__nv_bfloat16, false><<<grid, threads, C * sizeof(double), S(stream)>>>((const __nv_bfloat16*)t, nullptr, HW, C, pooled_sum);
+      ca_reduce_kernel<__nv_bfloat16, false><<<grid, l.threads, rs, S(stream)>>>((const __nv_bfloat16*)t, nullptr, HW, C, pooled_sum);
     SRB_LAUNCH_CHECK();
   }
   size_t smem = sizeof(float) * (2 * C + Cr);
   if (dtype == SRB_F32)
-    ca_scale_kernel<float><<<grid, threads, smem, S(stream)>>>((const float*)t, (const float*)skip, pooled_sum, HW, C, Cr,
-                                                               w1, b1, w2, b2, (float*)out, s_out, y_out);
+    ca_scale_kernel<float><<<grid, l.threads, smem, S(stream)>>>((const float*)t, (const float*)skip, pooled_sum, HW, C,
+                                                                 Cr, w1, b1, w2, b2, (float*)out, s_out, y_out);
   else
-    ca_scale_kernel<__nv_bfloat16><<<grid, threads, smem, S(stream)>>>((const __nv_bfloat16*)t, (const __nv_bfloat16*)skip,
-                                                                       pooled_sum, HW, C, Cr, w1, b1, w2, b2,
-                                                                       (__nv_bfloat16*)out, s_out, y_out);
+    ca_scale_kernel<__nv_bfloat16><<<grid, l.threads, smem, S(stream)>>>(
+        (const __nv_bfloat16*)t, (const __nv_bfloat16*)skip, pooled_sum, HW, C, Cr, w1, b1, w2, b2, (__nv_bfloat16*)out,
+        s_out, y_out);
   SRB_LAUNCH_CHECK();
   return 0;
 }
@@ -248,11 +365,11 @@ extern "C" int srb_ca_bwd(srb_ctx* ctx, int N, int H, int W, int C, int Cr, int 
                           float* scratch, int scratch_is_zero, int accumulate, void* stream) {
   SRB_REQUIRE(ctx && g && t && s && y && w1 && b1 && w2 && b2 && dt && dw1 && db1 && dw2 && db2 && scratch,
               "srb_ca_bwd: null argument");
-  SRB_REQUIRE(C % 4 == 0 && C <= 1024 && Cr >= 1 && Cr <= 64, "srb_ca_bwd: unsupported C=%d Cr=%d", C, Cr);
+  int rc = ca_check(C, Cr, dtype, "srb_ca_bwd");
+  if (rc) return rc;
   const int HW = H * W;
-  const int threads = ca_block_threads(C);
-  const int slabs = ca_slabs(ctx, N, HW, threads, C);
-  dim3 grid(slabs, N);
+  const CaLaunch l = ca_launch(ctx, N, HW, C, dtype == SRB_F32 ? 4 : 8);
+  dim3 grid(l.slabs, N);
   cudaStream_t st = S(stream);
   if (!scratch_is_zero) SRB_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * (size_t)N * C, st));
   if (!accumulate) {
@@ -262,18 +379,20 @@ extern "C" int srb_ca_bwd(srb_ctx* ctx, int N, int H, int W, int C, int Cr, int 
     SRB_CHECK_CUDA(cudaMemsetAsync(db2, 0, sizeof(float) * C, st));
     if (colsum_dt) SRB_CHECK_CUDA(cudaMemsetAsync(colsum_dt, 0, sizeof(float) * C, st));
   }
-  size_t smem = sizeof(float) * (5 * C + 2 * Cr);
+  const size_t rs = sizeof(float) * (size_t)l.lanes * C;
+  const size_t smem = sizeof(float) * (4 * C + 2 * Cr) + (colsum_dt ? rs : 0);
   if (dtype == SRB_F32) {
-    ca_reduce_kernel<float, true><<<grid, threads, C * sizeof(double), st>>>((const float*)g, (const float*)t, HW, C, scratch);
+    ca_reduce_kernel<float, true><<<grid, l.threads, rs, st>>>((const float*)g, (const float*)t, HW, C, scratch);
     SRB_LAUNCH_CHECK();
-    ca_bwd_apply_kernel<float><<<grid, threads, smem, st>>>((const float*)g, s, y, scratch, HW, C, Cr, w1, b1, w2, b2,
-                                                            (float*)dt, dw1, db1, dw2, db2, colsum_dt);
+    ca_bwd_apply_kernel<float><<<grid, l.threads, smem, st>>>((const float*)g, s, y, scratch, HW, C, Cr, w1, b1, w2, b2,
+                                                              (float*)dt, dw1, db1, dw2, db2, colsum_dt);
   } else {
-    ca_reduce_kernel<__nv_bfloat16, true><<<grid, threads, C * sizeof(double), st>>>((const __nv_bfloat16*)g,
-                                                                                     (const __nv_bfloat16*)t, HW, C, scratch);
+    ca_reduce_kernel<__nv_bfloat16, true><<<grid, l.threads, rs, st>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)t,
+                                                                        HW, C, scratch);
     SRB_LAUNCH_CHECK();
-    ca_bwd_apply_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>((const __nv_bfloat16*)g, s, y, scratch, HW, C, Cr, w1,
-                                                                    b1, w2, b2, (__nv_bfloat16*)dt, dw1, db1, dw2, db2, colsum_dt);
+    ca_bwd_apply_kernel<__nv_bfloat16><<<grid, l.threads, smem, st>>>((const __nv_bfloat16*)g, s, y, scratch, HW, C, Cr,
+                                                                      w1, b1, w2, b2, (__nv_bfloat16*)dt, dw1, db1, dw2,
+                                                                      db2, colsum_dt);
   }
   SRB_LAUNCH_CHECK();
   return 0;

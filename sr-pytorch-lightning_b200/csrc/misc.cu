@@ -256,48 +256,42 @@ __global__ void unshuffle_kernel(const T* __restrict__ g, int g_cs, int g_co, T*
   }
 }
 
-extern "C" int srb_pixel_unshuffle(srb_ctx* ctx, const void* g, int g_cs, int g_co, void* out, int o_cs, int o_co, int N,
-                                   int H, int W, int Cp, int r, int dtype, void* stream) {
-  SRB_REQUIRE(ctx && g && out, "srb_pixel_unshuffle: null argument");
-  int64_t total = (int64_t)N * H * W * r * r * Cp;
-  int blocks = srb_cdiv(total, 256);
-  if (blocks > 148 * 32) blocks = 148 * 32;
-  if (dtype == SRB_F32)
-    unshuffle_kernel<float><<<blocks, 256, 0, S(stream)>>>((const float*)g, g_cs, g_co, (float*)out, o_cs, o_co, N, H, W, Cp, r);
-  else
-    unshuffle_kernel<__nv_bfloat16><<<blocks, 256, 0, S(stream)>>>((const __nv_bfloat16*)g, g_cs, g_co,
-                                                                    (__nv_bfloat16*)out, o_cs, o_co, N, H, W, Cp, r);
-  SRB_LAUNCH_CHECK();
-  return 0;
-}
-
-// out = (act > 0) ? g : 0 over channel slices (ReLU backward, reference: autograd of nn.ReLU)
 template <typename T>
-__global__ void relu_bwd_kernel(const T* __restrict__ g, int g_cs, int g_co, const T* __restrict__ act, int a_cs,
-                                int a_co, T* __restrict__ out, int o_cs, int o_co, int C, int64_t npix) {
-  int64_t total = npix * C;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t p = i / C;
-    int c = (int)(i % C);
-    float a = ld_elem(act + p * a_cs + a_co + c);
-    float v = ld_elem(g + p * g_cs + g_co + c);
-    st_elem(out + p * o_cs + o_co + c, a > 0.f ? v : 0.f);
+__global__ void unshuffle_vec_kernel(const T* __restrict__ g, int g_cs, int g_co, T* __restrict__ out, int o_cs, int o_co,
+                                     int N, int H, int W, int Cp, int r) {
+  // one 16-byte channel vector per thread; consecutive threads walk channels, then (i,j), then pixels
+  using V = VecT<T>;
+  const int rr = r * r, cv = Cp / V::W;
+  const int64_t total = (int64_t)N * H * W * rr * cv;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cv) * V::W;
+    const int ij = (int)((idx / cv) % rr);
+    const int64_t p = idx / ((int64_t)cv * rr);
+    const int w = (int)(p % W);
+    const int h = (int)((p / W) % H);
+    const int64_t n = p / ((int64_t)W * H);
+    const int i = ij / r, j = ij % r;
+    const int64_t gp = (n * (H * r) + (h * r + i)) * (int64_t)(W * r) + (w * r + j);
+    *reinterpret_cast<typename V::raw*>(out + p * o_cs + o_co + ij * Cp + c) =
+        *reinterpret_cast<const typename V::raw*>(g + gp * g_cs + g_co + c);
   }
 }
 
-extern "C" int srb_relu_bwd(srb_ctx* ctx, const void* g, int g_cs, int g_co, const void* act, int a_cs, int a_co,
-                            void* out, int o_cs, int o_co, int C, int64_t npix, int dtype, void* stream) {
-  SRB_REQUIRE(ctx && g && act && out, "srb_relu_bwd: null argument");
-  int64_t total = npix * C;
+extern "C" int srb_pixel_unshuffle(srb_ctx* ctx, const void* g, int g_cs, int g_co, void* out, int o_cs, int o_co, int N,
+                                   int H, int W, int Cp, int r, int dtype, void* stream) {
+  SRB_REQUIRE(ctx && g && out, "srb_pixel_unshuffle: null argument");
+  const int vw = dtype == SRB_F32 ? 4 : 8;
+  const bool vec = (Cp % vw == 0) && (g_cs % vw == 0) && (g_co % vw == 0) && (o_cs % vw == 0) && (o_co % vw == 0);
+  int64_t total = (int64_t)N * H * W * r * r * (vec ? Cp / vw : Cp);
   int blocks = srb_cdiv(total, 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  if (dtype == SRB_F32)
-    relu_bwd_kernel<float><<<blocks, 256, 0, S(stream)>>>((const float*)g, g_cs, g_co, (const float*)act, a_cs, a_co,
-                                                          (float*)out, o_cs, o_co, C, npix);
-  else
-    relu_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, S(stream)>>>((const __nv_bfloat16*)g, g_cs, g_co,
-                                                                  (const __nv_bfloat16*)act, a_cs, a_co,
-                                                                  (__nv_bfloat16*)out, o_cs, o_co, C, npix);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (dtype == SRB_F32) {
+    if (vec) unshuffle_vec_kernel<float><<<blocks, 256, 0, S(stream)>>>((const float*)g, g_cs, g_co, (float*)out, o_cs, o_co, N, H, W, Cp, r);
+    else unshuffle_kernel<float><<<blocks, 256, 0, S(stream)>>>((const float*)g, g_cs, g_co, (float*)out, o_cs, o_co, N, H, W, Cp, r);
+  } else {
+    if (vec) unshuffle_vec_kernel<__nv_bfloat16><<<blocks, 256, 0, S(stream)>>>((const __nv_bfloat16*)g, g_cs, g_co, (__nv_bfloat16*)out, o_cs, o_co, N, H, W, Cp, r);
+    else unshuffle_kernel<__nv_bfloat16><<<blocks, 256, 0, S(stream)>>>((const __nv_bfloat16*)g, g_cs, g_co, (__nv_bfloat16*)out, o_cs, o_co, N, H, W, Cp, r);
+  }
   SRB_LAUNCH_CHECK();
   return 0;
 }

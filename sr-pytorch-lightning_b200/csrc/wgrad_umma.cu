@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_umma_kernel(const __grid_co
       if (a < 3) { kh = half; kw = a; }
       else if (a == 3) { kh = 2; kw = half; }
       else { kh = 2; kw = 2; }
-      const bool live = !(a == 4 && half == 1);
+      const bool live = !(a == 4 && half == 1) && ci < B.Cin;
 #pragma unroll 1
       for (int c0 = 0; c0 < 64; c0 += 32) {
         uint32_t acc[32];
@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_umma_kernel(const __grid_co
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int cop = B.co0 + c0 + j;                      // channel in gy's order
+            if (cop >= B.Cout) continue;
             const int co = rr > 1 ? (cop % Cp) * rr + cop / Cp : cop;
             float* dst = B.dw + (((int64_t)co * B.Cin + ci) * 3 + kh) * 3 + kw;
             const float v = __uint_as_float(acc[j]) * B.alpha;
@@ -203,7 +204,7 @@ int encode_act_map(srb_ctx* ctx, CUtensorMap* map, const void* base, int N, int 
 
 int srb_wgrad_umma_ok(const srb_wgrad_desc* d) {
   if (d->dtype != SRB_BF16 || d->ksize != 3) return 0;
-  if (d->Cin % 64 || d->Cout % 64 || d->Cin < 64 || d->Cout < 64) return 0;
+  if (d->Cin < 1 || d->Cout < 1) return 0;   // partial 64-channel blocks: TMA zero-fills, epilogue clips
   if (d->x_cs % 8 || d->x_co % 8 || d->g_cs % 8 || d->g_co % 8) return 0;
   if (d->W < 8) return 0;
   if (d->shuffle > 1 && (d->Cout % (d->shuffle * d->shuffle))) return 0;
@@ -229,8 +230,8 @@ int srb_wgrad_umma_batched(srb_ctx* ctx, const srb_wgrad_desc* descs, const void
     rc = encode_act_map(ctx, &tmG, gys[i], d.N, d.H, d.W, d.g_cs, d.g_co + d.Cout, kTH);
     if (rc) return rc;
     const int tiles_w = srb_cdiv(d.W, kTW), tiles_h = srb_cdiv(d.H, kTH);
-    for (int cb = 0; cb < d.Cin / 64; ++cb) {
-      for (int ob = 0; ob < d.Cout / 64; ++ob) {
+    for (int cb = 0; cb < srb_cdiv(d.Cin, 64); ++cb) {
+      for (int ob = 0; ob < srb_cdiv(d.Cout, 64); ++ob) {
         WgradBlock B;
         B.tmX = tmX;
         B.tmG = tmG;
@@ -291,7 +292,7 @@ int srb_colsum_launch(srb_ctx* ctx, const void* x, int cs, int co, int C, int64_
 
 int srb_wgrad_umma(srb_ctx* ctx, const srb_wgrad_desc* d, const void* x, const void* gy, float* dw, float* dbias,
                    cudaStream_t st) {
-  SRB_REQUIRE(srb_wgrad_umma_ok(d), "srb_conv_wgrad(umma): not eligible (bf16, k=3, Cin,Cout %% 64 == 0, W >= 8)");
+  SRB_REQUIRE(srb_wgrad_umma_ok(d), "srb_conv_wgrad(umma): not eligible (bf16, k=3, channel strides %% 8 == 0, W >= 8)");
   int rc = srb_wgrad_umma_batched(ctx, d, &x, &gy, &dw, 1, st);
   if (rc) return rc;
   if (dbias)  // bias gradient = per-channel sums of gy (gy's channel order -> parameter order)

@@ -40,4 +40,4 @@ class EDSR(SRModel):
         res = blocks[-1](res, residual=x)           # body tail conv + global skip (edsr.py:46-47)
         y = self.tail[0](res)
         y = self.tail[1](y)
-        return F200.ToNCHW.apply(y, self.add_mean.channel_add() if rgb else None)
+        return F200.ToNCHW.apply(y, self.add_mean.channel_add() if rgb else None, self._channels)

@@ -92,4 +92,4 @@ class RCAN(SRModel):
         res = mods[-1](res, residual=x)
         y = self.tail[0](res)
         y = self.tail[1](y)
-        return F200.ToNCHW.apply(y, self.add_mean.channel_add() if rgb else None)
+        return F200.ToNCHW.apply(y, self.add_mean.channel_add() if rgb else None, self._channels)

@@ -80,4 +80,4 @@ class RDN(SRModel):
             else:
                 x = mods[i](x)
                 i += 1
-        return F200.ToNCHW.apply(x, None)
+        return F200.ToNCHW.apply(x, None, self.UPNet[-1].out_channels)

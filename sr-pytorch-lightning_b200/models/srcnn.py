@@ -28,4 +28,4 @@ class SRCNN(SRModel):
         x = self._net[0](x, relu=True)
         x = self._net[2](x, relu=True)
         x = self._net[4](x)
-        return F200.ToNCHW.apply(x, None)
+        return F200.ToNCHW.apply(x, None, self._channels)

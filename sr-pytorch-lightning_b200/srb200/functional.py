@@ -30,13 +30,24 @@ def _grad_target(p: torch.Tensor):
     return buf, False, buf
 
 
+def _padded(c: int, dtype) -> int:
+    """Channel stride used for a c-channel NHWC tensor: bf16 tensors keep pixels 16-byte aligned
+    (multiple of 8 channels) so that TMA can address them — the 3-channel RGB tensors at the model
+    boundary are stored 8 wide; the extra channels are never read (TMA clips at the logical extent)."""
+    if dtype == torch.bfloat16 and c % 8:
+        return (c + 7) // 8 * 8
+    return c
+
+
 class ToNHWC(Function):
     """NCHW fp32 -> NHWC compute dtype, with MeanShift (common.py:58-71) as a per-channel add."""
 
     @staticmethod
     def forward(ctx, x, chan_add, dtype):
-        ctx.c = x.shape[1]
-        return ops.nchw_to_nhwc(x.contiguous().float(), chan_add, dtype)
+        n, c, h, w = x.shape
+        ctx.c = c
+        out = torch.empty((n, h, w, _padded(c, dtype)), dtype=dtype, device=x.device)
+        return ops.nchw_to_nhwc(x.contiguous().float(), chan_add, dtype, out=out)
 
     @staticmethod
     def backward(ctx, g):
@@ -47,29 +58,33 @@ class ToNCHW(Function):
     """NHWC compute dtype -> NCHW fp32, with add_mean (edsr.py:52, rcan.py:127) as a per-channel add."""
 
     @staticmethod
-    def forward(ctx, y, chan_add):
-        ctx.dtype = y.dtype
-        return ops.nhwc_to_nchw(y.contiguous(), 0, y.shape[3], chan_add)
+    def forward(ctx, y, chan_add, channels):
+        ctx.dtype, ctx.cs = y.dtype, y.shape[3]
+        return ops.nhwc_to_nchw(y.contiguous(), 0, channels, chan_add)
 
     @staticmethod
     def backward(ctx, g):
-        return ops.nchw_to_nhwc(g.contiguous().float(), None, ctx.dtype), None
+        n, c, h, w = g.shape
+        out = torch.empty((n, h, w, ctx.cs), dtype=ctx.dtype, device=g.device)
+        return ops.nchw_to_nhwc(g.contiguous().float(), None, ctx.dtype, out=out), None, None
 
 
 class ConvFn(Function):
     """y = [PixelShuffle_r]( relu?(conv_k(x) + b) * scale ) + residual?
 
     Covers DefaultConv2d / nn.Conv2d call sites (common.py:7-30; edsr.py:21-33; rcan.py:68,101;
-    rdn.py:57-59,71-72,87-93) together with the elementwise ops that follow them."""
+    rdn.py:57-59,71-72,87-93) together with the elementwise ops that follow them.  The logical
+    channel counts come from the weight; tensors may be wider (padded channel stride)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, residual, packs: PackedWeights, relu: bool, scale: float, shuffle: int):
         assert not (relu and (residual is not None or scale != 1.0)), "unsupported epilogue combination"
         x = x.contiguous()
-        n, h, w, cin = x.shape
-        cout, _, k, _ = weight.shape
+        n, h, w, _ = x.shape
+        cout, cin, k, _ = weight.shape
         r = shuffle if shuffle > 1 else 1
-        y = torch.empty((n, h * r, w * r, cout // (r * r)), dtype=x.dtype, device=x.device)
+        cp = cout // (r * r)
+        y = torch.empty((n, h * r, w * r, _padded(cp, x.dtype)), dtype=x.dtype, device=x.device)
         b = packs.get_bias(bias, shuffle) if bias is not None else None
         res = (residual.contiguous(), 0) if residual is not None else None
         ops.conv(x, 0, cin, packs, weight, b, y, 0, cout, k, relu=relu, scale=scale, shuffle=shuffle, res=res)
@@ -87,7 +102,7 @@ class ConvFn(Function):
         gm = g
         if relu:
             gm = torch.empty_like(g)
-            ops.relu_bwd(g, 0, y, 0, gm, 0, g.shape[3])
+            ops.relu_bwd(g, 0, y, 0, gm, 0, cout)
         if shuffle > 1:
             gm = ops.pixel_unshuffle(gm, shuffle)   # [N,H,W,Cout] in (ij, c') channel order
         dw = db = dx = None

@@ -19,8 +19,8 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-from . import lib as L
 from . import ops
+from .functional import _padded
 
 
 def partition_rows(h: int, parts: int):
@@ -100,10 +100,10 @@ class TiledEDSR:
     def _conv(self, conv, xs, *, relu=False, scale=1.0, residual=None, shuffle=0):
         outs = []
         for i, x in enumerate(xs):
-            n, h, w, cin = x.shape
-            cout = conv.weight.shape[0]
+            n, h, w, _ = x.shape
+            cout, cin = conv.weight.shape[0], conv.weight.shape[1]
             r = shuffle if shuffle > 1 else 1
-            y = torch.empty((n, h * r, w * r, cout // (r * r)), dtype=x.dtype, device=x.device)
+            y = torch.empty((n, h * r, w * r, _padded(cout // (r * r), x.dtype)), dtype=x.dtype, device=x.device)
             b = conv.packs.get_bias(conv.bias, shuffle)
             ops.conv(x, 0, cin, conv.packs, conv.weight, b, y, 0, cout, conv.kernel_size, relu=relu, scale=scale,
                      shuffle=shuffle, res=(residual[i], 0) if residual is not None else None)
@@ -127,9 +127,10 @@ class TiledEDSR:
         for i in mine:
             r0, r1 = parts[i]
             lo, hi = max(r0 - t, 0), min(r1 + t, H)
-            slab = ops.nchw_to_nhwc(x[:, :, lo:hi].contiguous(), add_in, m.act_dtype)
-            buf = torch.zeros((1, (r1 - r0) + 2 * t, x.shape[3], x.shape[1]), dtype=m.act_dtype, device=x.device)
-            buf[:, (lo - (r0 - t)):(lo - (r0 - t)) + (hi - lo)].copy_(slab)
+            cs = _padded(x.shape[1], m.act_dtype)
+            buf = torch.zeros((1, (r1 - r0) + 2 * t, x.shape[3], cs), dtype=m.act_dtype, device=x.device)
+            rows = buf[:, (lo - (r0 - t)):(lo - (r0 - t)) + (hi - lo)]     # contiguous row slab of buf
+            ops.nchw_to_nhwc(x[:, :, lo:hi].contiguous(), add_in, m.act_dtype, out=rows)
             xs.append(buf)
         conv = self._conv
         ex = lambda bufs, tt: self.ex.exchange(bufs, tt)  # noqa: E731
@@ -156,7 +157,7 @@ class TiledEDSR:
         add_out = m.add_mean.channel_add() if rgb else None
         for i, yy in zip(mine, y):
             owned = yy[:, t:yy.shape[1] - t].contiguous()
-            out[i] = ops.nhwc_to_nchw(owned, 0, owned.shape[3], add_out)
+            out[i] = ops.nhwc_to_nchw(owned, 0, m._channels, add_out)
         return out
 
     @torch.no_grad()

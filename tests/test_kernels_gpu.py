@@ -133,6 +133,14 @@ UMMA_CASES = [
     dict(n=1, h=16, w=16, cin=64, cout=192, k=3, x_cs=576, x_co=192, y_cs=576, y_co=0, residual=False),
     dict(n=1, h=16, w=16, cin=64, cout=32, k=3),                     # BN=32
     dict(n=1, h=5, w=40, cin=64, cout=64, k=3),                      # short & wide -> 16x8 tiles
+    dict(n=2, h=16, w=16, cin=3, cout=64, k=3, x_cs=8),              # head conv: partial K chunk, padded stride
+    dict(n=1, h=32, w=24, cin=64, cout=3, k=3, y_cs=8),              # tail conv: narrow output (N tile 16)
+    dict(n=1, h=32, w=24, cin=64, cout=3, k=3, y_cs=8, relu=True),
+    dict(n=1, h=16, w=16, cin=96, cout=32, k=3, x_cs=256, y_cs=256, y_co=96, relu=True),   # RDN-A dense layer
+    dict(n=3, h=48, w=48, cin=64, cout=64, k=3, residual=True),      # persistent kernel, >1 tile per CTA? (54 tiles)
+    dict(n=16, h=48, w=48, cin=64, cout=64, k=3, relu=True),         # 288 tiles on 148 SMs: 2 tiles per CTA
+    dict(n=16, h=48, w=48, cin=64, cout=64, k=3, colsum=2, mask=True),
+    dict(n=7, h=50, w=45, cin=64, cout=64, k=3, scale=0.5, residual=True),   # ragged, 3+ tiles per CTA
 ]
 
 
@@ -367,6 +375,9 @@ WGRAD_UMMA_CASES = [
     dict(n=1, h=16, w=16, cin=64, cout=256, shuffle=2),            # un-shuffled gradient channel order
     dict(n=2, h=16, w=16, cin=64, cout=64, alpha=0.1, accumulate=True),
     dict(n=1, h=16, w=16, cin=64, cout=64, x_cs=192, x_co=64, g_cs=128, g_co=64),   # channel slices
+    dict(n=2, h=16, w=16, cin=3, cout=64, x_cs=8),                 # head conv (partial ci block)
+    dict(n=1, h=32, w=24, cin=64, cout=3, g_cs=8),                 # tail conv (partial co block)
+    dict(n=1, h=16, w=16, cin=96, cout=32, x_cs=256, g_cs=256, g_co=96),   # RDN-A dense layer
 ]
 
 
