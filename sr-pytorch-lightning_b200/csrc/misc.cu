@@ -296,6 +296,37 @@ extern "C" int srb_pixel_unshuffle(srb_ctx* ctx, const void* g, int g_cs, int g_
   return 0;
 }
 
+// out = (act > 0) ? g : 0 over channel slices (ReLU backward, reference: autograd of nn.ReLU)
+template <typename T>
+__global__ void relu_bwd_kernel(const T* __restrict__ g, int g_cs, int g_co, const T* __restrict__ act, int a_cs,
+                                int a_co, T* __restrict__ out, int o_cs, int o_co, int C, int64_t npix) {
+  int64_t total = npix * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = i / C;
+    int c = (int)(i % C);
+    float a = ld_elem(act + p * a_cs + a_co + c);
+    float v = ld_elem(g + p * g_cs + g_co + c);
+    st_elem(out + p * o_cs + o_co + c, a > 0.f ? v : 0.f);
+  }
+}
+
+extern "C" int srb_relu_bwd(srb_ctx* ctx, const void* g, int g_cs, int g_co, const void* act, int a_cs, int a_co,
+                            void* out, int o_cs, int o_co, int C, int64_t npix, int dtype, void* stream) {
+  SRB_REQUIRE(ctx && g && act && out, "srb_relu_bwd: null argument");
+  int64_t total = npix * C;
+  int blocks = srb_cdiv(total, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (dtype == SRB_F32)
+    relu_bwd_kernel<float><<<blocks, 256, 0, S(stream)>>>((const float*)g, g_cs, g_co, (const float*)act, a_cs, a_co,
+                                                          (float*)out, o_cs, o_co, C, npix);
+  else
+    relu_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, S(stream)>>>((const __nv_bfloat16*)g, g_cs, g_co,
+                                                                  (const __nv_bfloat16*)act, a_cs, a_co,
+                                                                  (__nv_bfloat16*)out, o_cs, o_co, C, npix);
+  SRB_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // per-channel sums
 // ---------------------------------------------------------------------------------------------
