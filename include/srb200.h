@@ -197,6 +197,12 @@ int  srb_adam_step(srb_ctx*, float* param, const float* grad, float* m, float* v
                    const int32_t* step_dev, float grad_scale, void* stream);
 int  srb_inc_counter(srb_ctx*, int32_t* counter, void* stream);
 
+/* ---- diagnostics (not on the product path) -------------------------------------------------
+ * tcgen05.mma throughput probe: `blocks` CTAs each issue `iters` MMAs 128 x N x 16 (bf16, SS,
+ * 128-B swizzle; mn_major selects the operand major-ness) and write their elapsed SM cycles. */
+int  srb_probe_umma(srb_ctx*, int N, int iters, int mn_major, int distinct, int blocks,
+                    long long* cycles_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

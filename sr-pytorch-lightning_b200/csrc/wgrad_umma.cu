@@ -45,12 +45,13 @@ struct alignas(64) WgradBlock {
   int shuffle;
   int rmw;              // 1: dw += (non-atomic, S == 1 and accumulate)
   float alpha;
+  int cta0, S;          // this block is processed by CTAs [cta0, cta0 + S) of the launch, each
+                        // taking every S-th pixel tile (S proportional to the block's tile count)
 };
 
 struct WgradParams {
   WgradBlock blk[kMaxBlocks];
   int nblocks;
-  int S;                // CTAs per block (split over tiles)
 };
 
 __global__ void __launch_bounds__(kThreads, 1) wgrad_umma_kernel(const __grid_constant__ WgradParams P) {
@@ -61,11 +62,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_umma_kernel(const __grid_co
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bi = blockIdx.x / P.S, split = blockIdx.x % P.S;
+  int bi = 0;
+  while (bi + 1 < P.nblocks && (int)blockIdx.x >= P.blk[bi + 1].cta0) ++bi;
   const WgradBlock& B = P.blk[bi];
+  const int S = B.S, split = (int)blockIdx.x - B.cta0;
   const uint32_t ring = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   // tiles of this CTA: split, split + S, ...
-  const int my_tiles = (B.ntiles - split + P.S - 1) / P.S;
+  const int my_tiles = (B.ntiles - split + S - 1) / S;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_umma_kernel(const __grid_co
       ptx::prefetch_tensormap(&B.tmX);
       ptx::prefetch_tensormap(&B.tmG);
       for (int it = 0; it < my_tiles; ++it) {
-        const int t = split + it * P.S;
+        const int t = split + it * S;
         const int tw_i = t % B.tiles_w, th_i = (t / B.tiles_w) % B.tiles_h, n = t / (B.tiles_w * B.tiles_h);
         const int h0 = th_i * kTH, w0 = tw_i * kTW;
         const int s = it % kStages;
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_umma_kernel(const __grid_co
             const int co = rr > 1 ? (cop % Cp) * rr + cop / Cp : cop;
             float* dst = B.dw + (((int64_t)co * B.Cin + ci) * 3 + kh) * 3 + kw;
             const float v = __uint_as_float(acc[j]) * B.alpha;
-            if (P.S > 1) atomicAdd(dst, v);       // split reduction (dW pre-zeroed or accumulated)
+            if (S > 1) atomicAdd(dst, v);       // split reduction (dW pre-zeroed or accumulated)
             else if (B.rmw) *dst += v;            // whole reduction here, gradient accumulation
             else *dst = v;
           }
@@ -221,7 +224,6 @@ int srb_wgrad_umma_batched(srb_ctx* ctx, const srb_wgrad_desc* descs, const void
     attr_set = true;
   }
   std::vector<WgradBlock> blocks;
-  int min_tiles = 1 << 30;
   for (int i = 0; i < n_items; ++i) {
     const srb_wgrad_desc& d = descs[i];
     CUtensorMap tmX, tmG;  // one pair per layer; its 64x64 blocks differ by channel coordinates only
@@ -248,34 +250,51 @@ int srb_wgrad_umma_batched(srb_ctx* ctx, const srb_wgrad_desc* descs, const void
         B.shuffle = d.shuffle;
         B.rmw = d.accumulate ? 1 : 0;
         B.alpha = d.alpha;
-        if (B.ntiles < min_tiles) min_tiles = B.ntiles;
         blocks.push_back(B);
       }
     }
   }
   const int total = (int)blocks.size();
   if (total == 0) return 0;
-  // CTAs per block: fill the SMs, but keep several tiles per CTA (the epilogue costs ~40k global
-  // updates per CTA whatever its share of the reduction)
-  const int per_launch = total < kMaxBlocks ? total : kMaxBlocks;
-  int S = ctx->num_sms / per_launch;
-  if (S > 16) S = 16;
-  if (S > min_tiles) S = min_tiles;
-  if (S < 1) S = 1;
-  if (S > 1) {
-    // split reduction: CTAs add into dW with red.global.add, so overwritten layers start from zero
+  // Group the blocks into launches of <= kMaxBlocks and give every block a number of CTAs
+  // proportional to its share of the launch's pixel tiles (one CTA per SM overall): a 192x192 tail
+  // layer has 16x the tiles of a 48x48 body layer and must not be left to one or two SMs.
+  bool any_split = false;
+  std::vector<int> launch_start;
+  for (int b0 = 0; b0 < total; b0 += kMaxBlocks) {
+    launch_start.push_back(b0);
+    const int nb = total - b0 < kMaxBlocks ? total - b0 : kMaxBlocks;
+    long long tiles = 0;
+    for (int b = 0; b < nb; ++b) tiles += blocks[b0 + b].ntiles;
+    int cta = 0;
+    for (int b = 0; b < nb; ++b) {
+      WgradBlock& B = blocks[b0 + b];
+      long long s = ((long long)B.ntiles * ctx->num_sms + tiles / 2) / (tiles > 0 ? tiles : 1);
+      if (s < 1) s = 1;
+      if (s > B.ntiles) s = B.ntiles;
+      if (s > 96) s = 96;
+      B.S = (int)s;
+      B.cta0 = cta;
+      cta += B.S;
+      if (B.S > 1) any_split = true;
+    }
+  }
+  if (any_split) {
+    // split reductions add into dW with red.global.add, so overwritten layers start from zero
     for (int i = 0; i < n_items; ++i)
       if (!descs[i].accumulate)
         SRB_CHECK_CUDA(cudaMemsetAsync(dws[i], 0, sizeof(float) * (size_t)descs[i].Cout * descs[i].Cin * 9, st));
+    for (auto& B : blocks) B.rmw = 1;
   }
   WgradParams* P = new WgradParams();
   int rc = 0;
-  for (int b0 = 0; b0 < total && rc == 0; b0 += kMaxBlocks) {
+  for (size_t li = 0; li < launch_start.size() && rc == 0; ++li) {
+    const int b0 = launch_start[li];
     const int nb = total - b0 < kMaxBlocks ? total - b0 : kMaxBlocks;
     for (int b = 0; b < nb; ++b) P->blk[b] = blocks[b0 + b];
     P->nblocks = nb;
-    P->S = S;
-    wgrad_umma_kernel<<<nb * S, kThreads, smem, st>>>(*P);
+    const int ctas = P->blk[nb - 1].cta0 + P->blk[nb - 1].S;
+    wgrad_umma_kernel<<<ctas, kThreads, smem, st>>>(*P);
     __atomic_fetch_add(&g_srb_launches, 1ull, __ATOMIC_RELAXED);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -360,9 +360,10 @@ def test_errors_are_reported_not_thrown():
     w = torch.zeros(64, 64, 4, 4, device=dev)
     with pytest.raises(RuntimeError, match="kernel size"):
         ops.conv(x, 0, 64, ops.PackedWeights(), w, None, y, 0, 64, 4)
-    w3 = torch.zeros(64, 48, 3, 3, device=dev)
-    with pytest.raises(RuntimeError, match="not eligible"):
-        ops.conv(x, 0, 48, ops.PackedWeights(), w3, None, y, 0, 64, 3, backend=L.BACKEND_UMMA)
+    xf = torch.zeros(1, 8, 8, 64, device=dev)
+    w3 = torch.zeros(64, 64, 3, 3, device=dev)
+    with pytest.raises(RuntimeError, match="not eligible"):        # the tcgen05 path is bf16-only
+        ops.conv(xf, 0, 64, ops.PackedWeights(), w3, None, torch.zeros_like(xf), 0, 64, 3, backend=L.BACKEND_UMMA)
     with pytest.raises(RuntimeError, match="CUDA tensors"):
         ops.nchw_to_nhwc(torch.zeros(1, 3, 4, 4), None, torch.float32)
 
