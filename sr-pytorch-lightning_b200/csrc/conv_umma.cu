@@ -257,15 +257,15 @@ __global__ void __launch_bounds__(kThreads) conv_umma_kernel(const __grid_consta
         const uint32_t ph = (it / p.num_stages) & 1;
         ptx::mbar_wait(&full_bar[s], ph);
         ptx::tc_fence_after();
-        const uint32_t a_base = ring + (uint32_t)s * p.stage_bytes;
-        const uint32_t b_base = a_base + p.a_bytes;
+        const uint32_t a_lo = ptx::smem_desc_lo(ring + (uint32_t)s * p.stage_bytes, 16u);
+        const uint32_t b_lo = ptx::smem_desc_lo(ring + (uint32_t)s * p.stage_bytes + p.a_bytes, 16u);
+        constexpr uint32_t hi = ptx::smem_desc_hi_sw128(1024u);
+        const uint32_t a_kh = (uint32_t)p.TW * 8u;        // one tile row of pixels, in 16-byte units
         for (int kh = 0; kh < p.KS; ++kh) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adesc = ptx::smem_desc_sw128(a_base + (uint32_t)(kh * p.TW) * 128u + k * 32u, 16u, 1024u);
-            const uint64_t bdesc = ptx::smem_desc_sw128(b_base + (uint32_t)(kh * BN) * 128u + k * 32u, 16u, 1024u);
-            ptx::umma_bf16(tmem_acc, adesc, bdesc, idesc, (uint32_t)((it | kh | k) != 0));
-          }
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_bf16_lohi(tmem_acc, a_lo + kh * a_kh + k * 2u, hi, b_lo + (uint32_t)kh * (BN * 8u) + k * 2u, hi, idesc,
+                                (uint32_t)((it | kh | k) != 0));
         }
         ptx::umma_commit(&empty_bar[s]);  // frees the stage when these MMAs have read it
       }
@@ -364,26 +364,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_resident_kernel(const _
     if (lane == 0 && my_tiles > 0) {
       constexpr uint32_t idesc = ptx::idesc_bf16_f32(kTileM, BN, 0, 0);
       ptx::mbar_wait(&w_full, 0);
+      const uint32_t w_lo = ptx::smem_desc_lo(wbase, 16u);
       int it = 0;
       for (int ti = 0; ti < my_tiles; ++ti) {
         const int buf = ti & 1;
         ptx::mbar_wait(&acc_empty[buf], ((uint32_t)(ti >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
         ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_acc + (uint32_t)(buf * BN);
         for (int kw = 0; kw < 3; ++kw, ++it) {
           const int s = it % kResStages;
           const uint32_t ph = (it / kResStages) & 1;
           ptx::mbar_wait(&a_full[s], ph);
           ptx::tc_fence_after();
-          const uint32_t a_base = ring + (uint32_t)s * p.a_bytes;
+          const uint32_t a_lo = ptx::smem_desc_lo(ring + (uint32_t)s * p.a_bytes, 16u);
+          const uint32_t b_lo = w_lo + (uint32_t)kw * (3u * BN * 8u);
+          constexpr uint32_t hi = ptx::smem_desc_hi_sw128(1024u);
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
-            const uint32_t b_base = wbase + (uint32_t)((kw * 3 + kh) * BN) * 128u;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t adesc = ptx::smem_desc_sw128(a_base + (uint32_t)(kh * p.TW) * 128u + k * 32u, 16u, 1024u);
-              const uint64_t bdesc = ptx::smem_desc_sw128(b_base + k * 32u, 16u, 1024u);
-              ptx::umma_bf16(tmem_acc + (uint32_t)(buf * BN), adesc, bdesc, idesc, (uint32_t)((kw | kh | k) != 0));
-            }
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_bf16_lohi(tmem_d, a_lo + kh * 64u + k * 2u, hi, b_lo + kh * (BN * 8u) + k * 2u, hi, idesc,
+                                  (kh | k) != 0 ? 1u : (uint32_t)(kw != 0));
           }
           ptx::umma_commit(&a_empty[s]);
         }

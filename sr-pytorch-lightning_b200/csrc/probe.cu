@@ -32,14 +32,14 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int N, int iters, in
   if (threadIdx.x == 0) {
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)mn_major << 15) | ((uint32_t)mn_major << 16) |
                            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t a0 = base, b0 = base + 48 * 1024;
+    const uint32_t a_lo = ptx::smem_desc_lo(base, mn_major ? 1024u : 16u);
+    const uint32_t b_lo = ptx::smem_desc_lo(base + 48 * 1024, mn_major ? 1024u : 16u);
+    constexpr uint32_t hi = ptx::smem_desc_hi_sw128(1024u);
+    const uint32_t step = distinct > 1 ? (mn_major ? 128u : 2u) : 0u;
     const long long t0 = clock64();
-    for (int i = 0; i < iters; ++i) {
-      // walk through `distinct` different operand slices so the test is not a single hot line
-      const uint32_t off = (uint32_t)(i % distinct) * (mn_major ? 2048u : 32u);
-      const uint64_t ad = ptx::smem_desc_sw128(a0 + off, mn_major ? 1024u : 16u, 1024u);
-      const uint64_t bd = ptx::smem_desc_sw128(b0 + off, mn_major ? 1024u : 16u, 1024u);
-      ptx::umma_bf16(tmem, ad, bd, idesc, 1u);
+    for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) ptx::umma_bf16_lohi(tmem, a_lo + u * step, hi, b_lo + u * step, hi, idesc, 1u);
     }
     ptx::umma_commit(&bar);
     ptx::mbar_wait(&bar, 0);

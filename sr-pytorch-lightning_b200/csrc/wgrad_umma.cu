@@ -117,21 +117,20 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_umma_kernel(const __grid_co
         ptx::tc_fence_after();
         const uint32_t base = ring + (uint32_t)s * kStageBytes;
         const uint32_t gbase = base + 3 * kABytes;
-#pragma unroll 1
-        for (int a = 0; a < 5; ++a) {
-          // accumulator a: two taps stacked along M.  a<3: (kh0,kw=a)+(kh1,kw=a), second atom one
-          // tile row (1024 B) further; a=3: (kh2,kw0)+(kh2,kw1), second atom in the next window;
-          // a=4: (kh2,kw2) + don't-care rows (upper 64 lanes are discarded by the epilogue)
-          uint32_t a0, lbo;
-          if (a < 3) { a0 = base + a * kABytes; lbo = 1024u; }
-          else if (a == 3) { a0 = base + 2 * kTW * 128; lbo = (uint32_t)kABytes; }
-          else { a0 = base + 2 * kABytes + 2 * kTW * 128; lbo = 1024u; }
+        // accumulator a: two taps stacked along M.  a<3: (kh0,kw=a)+(kh1,kw=a), second atom one
+        // tile row (1024 B) further; a=3: (kh2,kw0)+(kh2,kw1), second atom in the next window;
+        // a=4: (kh2,kw2) + don't-care rows (upper 64 lanes are discarded by the epilogue)
+        constexpr uint32_t hi = ptx::smem_desc_hi_sw128(1024u);
+        const uint32_t g_lo = ptx::smem_desc_lo(gbase, 1024u);
+        const uint32_t acc_flag = (uint32_t)(it != 0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {   // 8 x 16 pixels
-            const uint64_t adesc = ptx::smem_desc_sw128(a0 + j * 2048u, lbo, 1024u);
-            const uint64_t bdesc = ptx::smem_desc_sw128(gbase + j * 2048u, 1024u, 1024u);
-            ptx::umma_bf16(tmem_acc + (uint32_t)a * 64u, adesc, bdesc, idesc, (uint32_t)((it | j) != 0));
-          }
+        for (int a = 0; a < 5; ++a) {
+          const uint32_t a0 = a < 3 ? base + a * kABytes : (a == 3 ? base + 2 * kTW * 128 : base + 2 * kABytes + 2 * kTW * 128);
+          const uint32_t a_lo = ptx::smem_desc_lo(a0, a == 3 ? (uint32_t)kABytes : 1024u);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)   // 8 x 16 pixels
+            ptx::umma_bf16_lohi(tmem_acc + (uint32_t)a * 64u, a_lo + j * 128u, hi, g_lo + j * 128u, hi, idesc,
+                                j != 0 ? 1u : acc_flag);
         }
         ptx::umma_commit(&empty_bar[s]);
       }
