@@ -1,5 +1,6 @@
 // Context lifetime and error reporting of libsrb200 (C ABI in include/srb200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -36,6 +37,8 @@ extern "C" int srb_create(int device, srb_ctx** out) {
   c->num_sms = prop.multiProcessorCount;
   c->smem_optin = (int)prop.sharedMemPerBlockOptin;
   c->encode_tiled = nullptr;
+  c->weights_dirty = 1;
+  c->no_pdl = getenv("SRB200_NO_PDL") != nullptr;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);

@@ -13,6 +13,8 @@ struct srb_ctx {
   int num_sms;
   int smem_optin;
   void* encode_tiled;  // PFN_cuTensorMapEncodeTiled, resolved at srb_create
+  int weights_dirty;   // a pack kernel was launched since the last fully serialised conv launch (conv_c64.cu)
+  int no_pdl;          // SRB200_NO_PDL=1: never use programmatic dependent launch (A/B measurements)
 };
 
 void srb_set_error(const char* fmt, ...);

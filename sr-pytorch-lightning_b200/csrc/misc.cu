@@ -78,6 +78,7 @@ extern "C" int srb_pack_weight(srb_ctx* ctx, const float* w, int Cout, int Cin, 
                                int shuffle, void* out, void* stream) {
   SRB_REQUIRE(ctx && w && out, "srb_pack_weight: null argument");
   SRB_REQUIRE(shuffle == 0 || (Cout % (shuffle * shuffle)) == 0, "srb_pack_weight: Cout %d not divisible by r^2", Cout);
+  ctx->weights_dirty = 1;
   int64_t total = (int64_t)Cout * Cin * k * k;
   if (packing == SRB_PACK_SIMT) {
     int blocks = srb_cdiv(total, 256);
@@ -502,6 +503,7 @@ __global__ void pack_table_kernel(const srb_pack_item* __restrict__ table) {
 
 extern "C" int srb_pack_table(srb_ctx* ctx, const srb_pack_item* table_dev, int n, int64_t max_elems, void* stream) {
   SRB_REQUIRE(ctx && (table_dev || n == 0), "srb_pack_table: null argument");
+  ctx->weights_dirty = 1;
   if (n == 0) return 0;
   SRB_REQUIRE(n <= 65535, "srb_pack_table: too many items (%d)", n);
   int bx = srb_cdiv(max_elems, 256 * 4);
