@@ -203,6 +203,9 @@ int  srb_inc_counter(srb_ctx*, int32_t* counter, void* stream);
 int  srb_probe_umma(srb_ctx*, int N, int iters, int mn_major, int distinct, int blocks,
                     long long* cycles_dev, void* stream);
 
+/* per-CTA event clocks of the 3x3 64-channel conv kernel (16 int64 per CTA; NULL = off) */
+int  srb_debug_set_trace(srb_ctx*, long long* dev_buf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,7 @@ extern "C" int srb_create(int device, srb_ctx** out) {
   c->smem_optin = (int)prop.sharedMemPerBlockOptin;
   c->encode_tiled = nullptr;
   c->weights_dirty = 1;
+  c->trace = nullptr;
   c->no_pdl = getenv("SRB200_NO_PDL") != nullptr;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -58,3 +59,11 @@ extern "C" int srb_destroy(srb_ctx* ctx) {
 }
 
 extern "C" int srb_num_sms(const srb_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
+
+/* diagnostics: conv_c64 writes 16 int64 per CTA (event clocks relative to CTA start, see conv_c64.cu)
+ * into `buf` (device memory, >= 16 * num_sms int64) on every launch while it is set; NULL turns it off */
+extern "C" int srb_debug_set_trace(srb_ctx* ctx, long long* buf) {
+  SRB_REQUIRE(ctx, "srb_debug_set_trace: null context");
+  ctx->trace = buf;
+  return 0;
+}

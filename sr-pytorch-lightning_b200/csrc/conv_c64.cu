@@ -45,7 +45,16 @@ struct C64Params {
   int a_stages;                 // input-window ring depth
   int n_e;                      // epilogue operand tiles per output tile: [mask][residual]
   uint32_t off_a, off_e, off_o; // offsets from the 1024-aligned shared-memory base
+  long long* trace;             // diagnostics: per-CTA event clocks (srb_debug_set_trace), else NULL
 };
+
+// event slots of the per-CTA trace record (16 x int64 per CTA)
+enum { EV_T0_NS = 0, EV_PROLOGUE, EV_DEPWAIT, EV_WFULL, EV_A0FULL, EV_MMA0_ISSUED, EV_ACC0, EV_EPI0, EV_ACC1, EV_EPI1,
+       EV_STORED, EV_END, EV_T1_NS, EV_SMID };
+#define TRACE(ev)                                                                   \
+  do {                                                                              \
+    if (p.trace) p.trace[(size_t)blockIdx.x * 16 + (ev)] = clock64() - t_start;     \
+  } while (0)
 
 __device__ __forceinline__ void tile_coords(const C64Params& p, int t, int& n, int& h0, int& w0) {
   const int tw_i = t % p.tiles_w;
@@ -69,6 +78,13 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   // the next kernel of the stream may start its own prologue now (it cannot touch our outputs
   // before its griddepcontrol.wait, which waits for this whole grid)
   ptx::griddep_launch_dependents();
+  const long long t_start = clock64();
+  if (p.trace && threadIdx.x == 0) {
+    p.trace[(size_t)blockIdx.x * 16 + EV_T0_NS] = (long long)ptx::globaltimer_ns();
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.trace[(size_t)blockIdx.x * 16 + EV_SMID] = smid;
+  }
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -103,6 +119,7 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_acc = tmem_slot;
+  if (threadIdx.x == 0) TRACE(EV_PROLOGUE);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -117,6 +134,7 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         if (has_res) ptx::prefetch_tensormap(&tmR);
       }
       ptx::griddep_wait();   // activations below are written by the previous kernel(s)
+      TRACE(EV_DEPWAIT);
       for (int ti = 0; ti < my_tiles; ++ti) {
         int n, h0, w0;
         tile_coords(p, (int)blockIdx.x + ti * (int)gridDim.x, n, h0, w0);
@@ -144,6 +162,7 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       constexpr uint32_t hi_a = ptx::smem_desc_hi_sw128((uint32_t)kP * 128u);   // 8-pixel row groups, one window row apart
       constexpr uint32_t hi_b = ptx::smem_desc_hi_sw128(1024u);
       ptx::mbar_wait(&w_full, 0);
+      TRACE(EV_WFULL);
       const uint32_t w_lo = ptx::smem_desc_lo(wbase, 16u);
       for (int ti = 0; ti < my_tiles; ++ti) {
         const int buf = ti & 1;
@@ -151,6 +170,7 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const int s = ti % p.a_stages;
         ptx::mbar_wait(&a_full[s], ((uint32_t)(ti / p.a_stages)) & 1u);
         ptx::tc_fence_after();
+        if (ti == 0) TRACE(EV_A0FULL);
         const uint32_t tmem_d = tmem_acc + (uint32_t)(buf * 64);
         const uint32_t a_lo = ptx::smem_desc_lo(abase + (uint32_t)s * kWinStride, 16u);
 #pragma unroll
@@ -165,6 +185,7 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         }
         ptx::umma_commit(&a_empty[s]);
         ptx::umma_commit(&acc_full[buf]);
+        if (ti == 0) TRACE(EV_MMA0_ISSUED);
       }
     }
   } else {
@@ -193,6 +214,7 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       }
       ptx::mbar_wait(&acc_full[buf], par);
       ptx::tc_fence_after();
+      if (store_thread && ti < 2) TRACE(ti == 0 ? EV_ACC0 : EV_ACC1);
       if (p.n_e) ptx::mbar_wait(&e_full[buf], par);
 #pragma unroll 1
       for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -284,13 +306,21 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         ptx::tma_store_4d(&tmY, obase + (uint32_t)buf * kTileBytes, d.y_co, w0, h0, n);
         if (d.flags & SRB_OUT2) ptx::tma_store_4d(&tmY2, obase + (uint32_t)buf * kTileBytes, d.y2_co, w0, h0, n);
         ptx::bulk_commit_group();
+        if (ti < 2) TRACE(ti == 0 ? EV_EPI0 : EV_EPI1);
       }
     }
-    if (store_thread) ptx::bulk_wait_group<0>();   // all output bytes written before the grid completes
+    if (store_thread) {
+      ptx::bulk_wait_group<0>();   // all output bytes written before the grid completes
+      TRACE(EV_STORED);
+    }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (p.trace && threadIdx.x == 0) {
+    TRACE(EV_END);
+    p.trace[(size_t)blockIdx.x * 16 + EV_T1_NS] = (long long)ptx::globaltimer_ns();
+  }
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_acc, kTmemCols);
@@ -342,6 +372,7 @@ int srb_conv_c64(srb_ctx* ctx, const srb_conv_desc* d, const void* x, const void
   p.d = *d;
   p.bias = bias;
   p.colsum = colsum;
+  p.trace = ctx->trace;
   p.tiles_w = srb_cdiv(d->W, kTW);
   p.tiles_h = srb_cdiv(d->H, kTH);
   const int64_t tiles = (int64_t)d->N * p.tiles_w * p.tiles_h;

@@ -72,6 +72,7 @@ PROTOTYPES = {
     "srb_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_vp, c_f32, c_vp]),
     "srb_inc_counter": (c_i32, [c_vp, c_vp, c_vp]),
     "srb_probe_umma": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "srb_debug_set_trace": (c_i32, [c_vp, c_vp]),
 }
 
 _lib = None
