@@ -139,6 +139,66 @@ int  srb_conv_wgrad_batched(srb_ctx*, const srb_wgrad_item* items, int n, void* 
 int  srb_conv_uses_umma(const srb_conv_desc*);
 int  srb_wgrad_uses_umma(const srb_wgrad_desc*);
 
+/* ---- layer chains ---------------------------------------------------------------------------
+ * MANY dependent 64-channel layers in ONE persistent launch.  A single 3x3 64->64 conv on a
+ * 16 x 48x48 batch is ~1.8 us of tensor work but ~6.5 us as a dependent kernel (launch gap,
+ * prologue, filter reload, L2 round trip).  A chain runs a whole ResidualGroup (models/rcan.py:59-74:
+ * 20 x RCAB + conv + skip) or a stack of ResBlocks (common.py:74-109), forward or backward, as one
+ * kernel: every CTA owns fixed output tiles, filters stream through shared memory layer by layer,
+ * and per-(op, sample) counters in device memory order the layers; tiles of DIFFERENT samples
+ * interleave on an SM so one sample's store -> flag -> load latency hides behind another's MMAs.
+ *
+ * Tensors are slots of up to four "spaces", each a contiguous [slots][N][H][W][64] bf16 buffer;
+ * a buffer reference is (space << 14) | slot, SRB_CHAIN_NONE when unused.  Every slot is written
+ * by at most one op of a chain.  Op i (i > 0) may read what ops < i wrote; op 0 reads only data
+ * produced before the launch.
+ *
+ * SRB_CHAIN_CONV: y = epilogue(conv3x3(x)) with the srb_conv flag semantics (RELU, scale, MASK or
+ *   RESIDUAL tile `e`, COLSUM).  With SRB_CHAIN_CA the op is an RCAB's second conv fused with its
+ *   CALayer (rcan.py:10-29,54): t = conv(x)+bias is stored to y, its per-sample channel sums go to
+ *   colsum [N][64]; once the sample's sums are complete, out = t*gate + e is stored to y2 and the
+ *   pooled mean / gate are written to ca_s / ca_y [N][64] for backward.
+ * SRB_CHAIN_CA_BWD: CALayer + skip backward for one RCAB: x = t (saved), e = g (dL/dout);
+ *   y = dt = g*gate + ds/HW; parameter gradients are ACCUMULATED into ca_dw1..ca_db2, column sums
+ *   of dt into colsum [64] (the bias gradient of the conv that produced t); ca_scratch [N][64]
+ *   must be zero on entry.
+ * counters: n_ops * 2 * N int32, zero on entry. */
+enum { SRB_CHAIN_CONV = 0, SRB_CHAIN_CA_BWD = 1 };
+enum { SRB_CHAIN_CA = 32 };            /* extra flag bit for SRB_CHAIN_CONV ops */
+#define SRB_CHAIN_NONE 0xFFFFu
+#define SRB_CHAIN_MAX_OPS 64
+
+typedef struct srb_chain_op {
+  int32_t  kind;
+  uint32_t flags;
+  uint16_t x, y, e, y2;     /* buffer references */
+  int32_t  w_layer;         /* index into the packed filter bank (CONV) */
+  float    scale;
+  int32_t  colsum_groups;   /* 1 -> colsum[64]; N -> colsum[N][64] (always N with SRB_CHAIN_CA) */
+  int32_t  ca_cr;           /* hidden width of the CALayer (channel / reduction) */
+  const float* bias;        /* [64] or NULL */
+  float*   colsum;
+  const float *ca_w1, *ca_b1, *ca_w2, *ca_b2;   /* conv_du.0 [Cr][64], [Cr]; conv_du.2 [64][Cr], [64] */
+  float   *ca_s, *ca_y;                         /* [N][64]: written by SRB_CHAIN_CA, read by CA_BWD */
+  float   *ca_dw1, *ca_db1, *ca_dw2, *ca_db2;   /* CA_BWD: accumulated */
+  float   *ca_scratch;                          /* CA_BWD: [N][64] zero-filled */
+} srb_chain_op;
+
+typedef struct srb_chain_desc {
+  int32_t N, H, W;                    /* 64 channels, bf16 */
+  int32_t n_ops;
+  const srb_chain_op* ops;            /* host array */
+  void*   space_base[4];
+  int32_t space_slots[4];             /* 0 = space unused */
+  const void* weights;                /* SRB_PACK_UMMA filters, [n_layers][9][64][64] bf16 */
+  int32_t n_layers;
+  int32_t* counters;
+  int64_t* trace;                     /* diagnostics or NULL: [grid][2][n_ops][8] event times (ns) + [grid][4] (ns, clock) at start/end, see conv_chain.cu */
+} srb_chain_desc;
+int  srb_conv_chain(srb_ctx*, const srb_chain_desc*, void* stream);
+/* number of CTAs srb_conv_chain launches for this shape (size of the trace buffer's first dim) */
+int  srb_conv_chain_grid(const srb_ctx*, int N, int H, int W);
+
 /* ---- RCAN channel attention (models/rcan.py:10-29 CALayer + rcan.py:54 `res += x`) ---------
  * out = t * sigmoid(W2 relu(W1 mean_hw(t) + b1) + b2) + skip.
  * pooled_sum: [N][C] fp32 sums of t over H*W: an input (from srb_conv's COLSUM) when

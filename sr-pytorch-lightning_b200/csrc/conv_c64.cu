@@ -157,7 +157,7 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && my_tiles > 0) {
+    if (my_tiles > 0 && ptx::elect_one_sync()) {   // elect.sync: operands stay in uniform registers
       constexpr uint32_t idesc = ptx::idesc_bf16_f32(128, 64, 0, 0);
       constexpr uint32_t hi_a = ptx::smem_desc_hi_sw128((uint32_t)kP * 128u);   // 8-pixel row groups, one window row apart
       constexpr uint32_t hi_b = ptx::smem_desc_hi_sw128(1024u);

@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(kThreads) conv_umma_kernel(const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (ptx::elect_one_sync()) {
       constexpr uint32_t idesc = ptx::idesc_bf16_f32(kTileM, BN, 0, 0);
       for (int it = 0; it < iters; ++it) {
         const int s = it % p.num_stages;
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_resident_kernel(const _
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && my_tiles > 0) {
+    if (my_tiles > 0 && ptx::elect_one_sync()) {
       constexpr uint32_t idesc = ptx::idesc_bf16_f32(kTileM, BN, 0, 0);
       ptx::mbar_wait(&w_full, 0);
       const uint32_t w_lo = ptx::smem_desc_lo(wbase, 16u);

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_umma_kernel(const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && my_tiles > 0) {
+    if (my_tiles > 0 && ptx::elect_one_sync()) {
       // A and B both MN-major (bits 15, 16), M = 128, N = 64
       constexpr uint32_t idesc = ptx::idesc_bf16_f32(128, 64, 1, 1);
       for (int it = 0; it < my_tiles; ++it) {

@@ -53,8 +53,49 @@ class ResidualGroup(nn.Module):
         body.append(DefaultConv2d(n_feat, n_feat, kernel_size))
         self.body = nn.Sequential(*body)
 
+    def filter_bank(self, mode):
+        """Contiguous packed 3x3 filters of the group in chain order: (conv1, conv2) per RCAB, tail."""
+        from srb200 import ops
+        if not hasattr(self, "_bank"):
+            self._bank = ops.FilterBank()
+        mods = list(self.body)
+        convs = []
+        for blk in mods[:-1]:
+            convs.append((blk.body[0].weight, blk.body[0].packs))
+            convs.append((blk.body[2].weight, blk.body[2].packs))
+        convs.append((mods[-1].weight, mods[-1].packs))
+        return self._bank.get(convs, mode)
+
+    def _chain_ok(self, x) -> bool:
+        import torch
+        mods = list(self.body)
+        if not (F200.chain_enabled() and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[3] == 64):
+            return False
+        if len(mods) < 2:
+            return False
+        # the fused CALayer needs every tile of a sample on its own (CTA, chain): see srb_conv_chain
+        from srb200 import ops
+        n, h, w, _ = x.shape
+        if ((h + 15) // 16) * ((w + 7) // 8) > 2 * ops.chain_grid(x.device, n, h, w):
+            return False
+        for blk in mods[:-1]:
+            c1, c2, ca = blk.body[0], blk.body[2], blk.body[3]
+            if tuple(c1.weight.shape) != (64, 64, 3, 3) or tuple(c2.weight.shape) != (64, 64, 3, 3):
+                return False
+            if c1.bias is None or c2.bias is None or ca.conv_du[0].weight.shape[0] > 16:
+                return False
+        return tuple(mods[-1].weight.shape) == (64, 64, 3, 3) and mods[-1].bias is not None
+
     def forward(self, x):
         mods = list(self.body)
+        if self._chain_ok(x):
+            params = []
+            for blk in mods[:-1]:
+                c1, c2, ca = blk.body[0], blk.body[2], blk.body[3]
+                d0, d2 = ca.conv_du[0], ca.conv_du[2]
+                params += [c1.weight, c1.bias, c2.weight, c2.bias, d0.weight, d0.bias, d2.weight, d2.bias]
+            params += [mods[-1].weight, mods[-1].bias]
+            return F200.RCANGroupFn.apply(x, self, *params)
         res = x
         for blk in mods[:-1]:
             res = blk(res)

@@ -214,6 +214,113 @@ class RCABFn(Function):
         return dx, dw1, db1, dw2, db2, dcw1, dcb1, dcw2, dcb2, None, None
 
 
+def chain_enabled() -> bool:
+    """Layer-chain kernels (srb_conv_chain) are the default for the 64-channel bf16 trunks;
+    SRB200_NO_CHAIN=1 selects the one-launch-per-layer path (A/B measurements, debugging)."""
+    import os
+    return os.environ.get("SRB200_NO_CHAIN", "0") in ("", "0")
+
+
+def _zeroed_grad_target(p):
+    """Like _grad_target for gradients the kernels ACCUMULATE with atomics: the buffer is zero
+    unless it is a live slice of the flat gradient buffer."""
+    buf, acc, ret = _grad_target(p)
+    if not acc:
+        buf.zero_()
+    return buf, ret
+
+
+class RCANGroupFn(Function):
+    """RCAN ResidualGroup (rcan.py:59-74): n x RCAB (rcan.py:33-55) + conv + skip, forward and
+    backward each as ONE persistent chain launch (ops.Chain -> srb_conv_chain).
+
+    Forward space 0 ("A", saved for backward) holds, per RCAB b: slot 3b = relu(conv1), 3b+1 = t =
+    conv2 output (pre-attention), 3b+2 = block output; slot 3n = group output.  Backward space 0
+    ("B"): slot 3b = dt, 3b+1 = d(relu(conv1)) masked, 3b+2 = dL/d(block input); slot 3n = dL/d(last
+    block output).  params = per RCAB (w1, b1, w2, b2, ca_w1, ca_b1, ca_w2, ca_b2), then (w_tail, b_tail)."""
+
+    @staticmethod
+    def forward(ctx, x, owner, *params):
+        x = x.contiguous()
+        n, h, w, c = x.shape
+        assert c == 64 and x.dtype == torch.bfloat16
+        nb = (len(params) - 2) // 8
+        dev = x.device
+        A = torch.empty((3 * nb + 1, n, h, w, 64), dtype=x.dtype, device=dev)
+        s_all = torch.empty((nb, n, 64), dtype=torch.float32, device=dev)
+        y_all = torch.empty((nb, n, 64), dtype=torch.float32, device=dev)
+        pool = ops.zeros_f32((nb, n, 64), dev)
+        bank = owner.filter_bank(L.PACK_FWD)
+        ch = ops.Chain(n, h, w, dev)
+        ch.space(0, A)
+        ch.space(2, x.view(1, n, h, w, 64))
+        ref = ops.Chain.ref
+        xin = ref(2, 0)
+        cur = xin
+        for b in range(nb):
+            w1, b1, w2, b2, cw1, cb1, cw2, cb2 = (t.detach() for t in params[8 * b:8 * b + 8])
+            ch.conv(cur, ref(0, 3 * b), 2 * b, b1, relu=True)
+            ch.conv_ca(ref(0, 3 * b), ref(0, 3 * b + 1), ref(0, 3 * b + 2), cur, 2 * b + 1, b2, pool[b],
+                       cw1.reshape(cw1.shape[0], 64), cb1, cw2.reshape(64, cw2.shape[1]), cb2, s_all[b], y_all[b])
+            cur = ref(0, 3 * b + 2)
+        ch.conv(cur, ref(0, 3 * nb), 2 * nb, params[-1].detach(), res=xin)
+        ch.run(bank)
+        ctx.save_for_backward(x, A, s_all, y_all, *params)
+        ctx.owner, ctx.nb = owner, nb
+        return A[3 * nb]
+
+    @staticmethod
+    def backward(ctx, g):
+        x, A, s_all, y_all, *params = ctx.saved_tensors
+        nb, owner = ctx.nb, ctx.owner
+        g = g.contiguous()
+        _, n, h, w, _ = A.shape
+        dev = g.device
+        B = torch.empty((3 * nb + 1, n, h, w, 64), dtype=A.dtype, device=dev)
+        scratch = ops.zeros_f32((nb, n, 64), dev)
+        bank = owner.filter_bank(L.PACK_DGRAD)
+        ch = ops.Chain(n, h, w, dev)
+        ch.space(0, B)
+        ch.space(1, A)
+        ch.space(2, g.view(1, n, h, w, 64))
+        ref = ops.Chain.ref
+        grads = [None] * len(params)
+        wq = []   # (x tensor, gy tensor, weight index, bias index or None)
+        # group tail conv: out = conv(last) + x
+        ch.conv(ref(2, 0), ref(0, 3 * nb), 2 * nb)
+        wq.append((A[3 * nb - 1], g, len(params) - 2, len(params) - 1))
+        gref = ref(0, 3 * nb)
+        for b in range(nb - 1, -1, -1):
+            w1, b1, w2, b2, cw1, cb1, cw2, cb2 = params[8 * b:8 * b + 8]
+            db1, grads[8 * b + 1] = _zeroed_grad_target(b1)
+            db2, grads[8 * b + 3] = _zeroed_grad_target(b2)
+            dcw1, grads[8 * b + 4] = _zeroed_grad_target(cw1)
+            dcb1, grads[8 * b + 5] = _zeroed_grad_target(cb1)
+            dcw2, grads[8 * b + 6] = _zeroed_grad_target(cw2)
+            dcb2, grads[8 * b + 7] = _zeroed_grad_target(cb2)
+            cr = cw1.shape[0]
+            ch.ca_bwd(ref(1, 3 * b + 1), gref, ref(0, 3 * b), cw1.detach().reshape(cr, 64), cb1.detach(),
+                      cw2.detach().reshape(64, cr), cb2.detach(), s_all[b], y_all[b], dcw1.view(cr, 64), dcb1,
+                      dcw2.view(64, cr), dcb2, scratch[b], colsum_dt=db2)
+            ch.conv(ref(0, 3 * b), ref(0, 3 * b + 1), 2 * b + 1, mask=ref(1, 3 * b), colsum=db1, colsum_groups=1)
+            ch.conv(ref(0, 3 * b + 1), ref(0, 3 * b + 2), 2 * b, res=gref)
+            wq.append((A[3 * b], B[3 * b], 8 * b + 2, None))
+            wq.append((A[3 * b - 1] if b > 0 else x, B[3 * b + 1], 8 * b, None))
+            gref = ref(0, 3 * b + 2)
+        ch.run(bank)
+        for xt, gy, wi, bi in wq:
+            wbuf, acc, grads[wi] = _grad_target(params[wi])
+            bbuf = None
+            if bi is not None:
+                bbuf, _, grads[bi] = _grad_target(params[bi])
+            ops.conv_wgrad(xt, 0, 64, gy, 0, 64, 3, wbuf, bbuf, accumulate=acc)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(g)
+            ops.add_channels(B[2], 0, g, 0, dx, 0, 64)
+        return (dx, None, *grads)
+
+
 class RDBFn(Function):
     """RDN residual dense block (rdn.py:24-40).  The C dense layers read a channel prefix of ONE
     [N,H,W,G0+C*G] buffer and write their G new channels in place (no torch.cat, rdn.py:21);

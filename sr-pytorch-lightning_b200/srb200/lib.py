@@ -38,6 +38,26 @@ class PackItem(C.Structure):
     _fields_ = [("src", c_vp), ("dst", c_vp)] + [(n, c_i32) for n in ("Cout", "Cin", "ksize", "packing", "mode", "shuffle")]
 
 
+CHAIN_CONV, CHAIN_CA_BWD = 0, 1
+CHAIN_CA = 32
+CHAIN_NONE = 0xFFFF
+CHAIN_MAX_OPS = 64
+
+
+class ChainOp(C.Structure):
+    _fields_ = [("kind", c_i32), ("flags", C.c_uint32), ("x", C.c_uint16), ("y", C.c_uint16), ("e", C.c_uint16),
+                ("y2", C.c_uint16), ("w_layer", c_i32), ("scale", c_f32), ("colsum_groups", c_i32), ("ca_cr", c_i32),
+                ("bias", c_vp), ("colsum", c_vp), ("ca_w1", c_vp), ("ca_b1", c_vp), ("ca_w2", c_vp), ("ca_b2", c_vp),
+                ("ca_s", c_vp), ("ca_y", c_vp), ("ca_dw1", c_vp), ("ca_db1", c_vp), ("ca_dw2", c_vp), ("ca_db2", c_vp),
+                ("ca_scratch", c_vp)]
+
+
+class ChainDesc(C.Structure):
+    _fields_ = [("N", c_i32), ("H", c_i32), ("W", c_i32), ("n_ops", c_i32), ("ops", C.POINTER(ChainOp)),
+                ("space_base", c_vp * 4), ("space_slots", c_i32 * 4), ("weights", c_vp), ("n_layers", c_i32),
+                ("counters", c_vp), ("trace", c_vp)]
+
+
 class WgradItem(C.Structure):
     _fields_ = [("d", WgradDesc), ("x", c_vp), ("gy", c_vp), ("dw", c_vp), ("dbias", c_vp)]
 
@@ -58,6 +78,8 @@ PROTOTYPES = {
     "srb_conv_wgrad_batched": (c_i32, [c_vp, C.POINTER(WgradItem), c_i32, c_vp]),
     "srb_conv_uses_umma": (c_i32, [C.POINTER(ConvDesc)]),
     "srb_wgrad_uses_umma": (c_i32, [C.POINTER(WgradDesc)]),
+    "srb_conv_chain": (c_i32, [c_vp, C.POINTER(ChainDesc), c_vp]),
+    "srb_conv_chain_grid": (c_i32, [c_vp, c_i32, c_i32, c_i32]),
     "srb_ca_fwd": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32] + [c_vp] * 8),
     "srb_ca_bwd": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32] + [c_vp] * 15 + [c_i32, c_i32, c_vp]),
     "srb_pack_table": (c_i32, [c_vp, c_vp, c_i32, c_i64, c_vp]),

@@ -45,13 +45,16 @@ def dtype_code(t):
 # --------------------------------------------------------------------------------------------
 # weights
 # --------------------------------------------------------------------------------------------
-def pack_weight(w: torch.Tensor, packing: int, mode: int, shuffle: int = 0) -> torch.Tensor:
-    """fp32 OIHW parameter -> packed device buffer (uint8 tensor)."""
+def pack_weight(w: torch.Tensor, packing: int, mode: int, shuffle: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
+    """fp32 OIHW parameter -> packed device buffer (uint8 tensor; `out` = caller-provided slice)."""
     lib = L.load()
     assert w.dtype == torch.float32 and w.is_contiguous()
     cout, cin, k, _ = w.shape
     nbytes = lib.srb_packed_weight_bytes(cout, cin, k, packing, mode)
-    out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    if out is None:
+        out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    else:
+        assert out.dtype == torch.uint8 and out.numel() == nbytes and out.is_contiguous() and out.device == w.device
     L.check(lib.srb_pack_weight(_ctx(w), _p(w), cout, cin, k, packing, mode, shuffle, _p(out), _stream()), "srb_pack_weight")
     return out
 
@@ -87,15 +90,18 @@ class PackedWeights:
         self._cache = {}
         _all_packs.add(self)
 
-    def get(self, w: torch.Tensor, packing: int, mode: int, shuffle: int = 0):
-        key = (packing, mode, shuffle)
+    def get(self, w: torch.Tensor, packing: int, mode: int, shuffle: int = 0, out: torch.Tensor | None = None):
+        """`out`: pack into this caller-owned slice (a layer of a chain's filter bank) instead of a
+        private buffer; such entries live under their own cache key."""
+        key = (packing, mode, shuffle) if out is None else (packing, mode, shuffle, "bank")
         hit = self._cache.get(key)
-        if hit is not None and _managed and hit[2].data_ptr() == w.data_ptr():
+        same_home = hit is not None and (out is None or hit[1].data_ptr() == out.data_ptr())
+        if same_home and _managed and hit[2].data_ptr() == w.data_ptr():
             return hit[1]
         tag = (w.data_ptr(), w._version, w.device, _generation)
-        if hit is not None and hit[0] == tag:
+        if same_home and hit[0] == tag:
             return hit[1]
-        packed = pack_weight(w.detach(), packing, mode, shuffle)
+        packed = pack_weight(w.detach(), packing, mode, shuffle, out=out)
         self._cache[key] = (tag, packed, w.detach())
         return packed
 
@@ -133,7 +139,7 @@ class PackTable:
                 if key[0] == "bias":
                     rows.append((src.data_ptr(), packed.data_ptr(), src.numel(), 1, 0, 0, 0, key[1]))
                 else:
-                    packing, mode, shuffle = key
+                    packing, mode, shuffle = key[:3]
                     cout, cin, k, _ = src.shape
                     rows.append((src.data_ptr(), packed.data_ptr(), cout, cin, k, packing, mode, shuffle))
                     max_elems = max(max_elems, src.numel())
@@ -441,3 +447,131 @@ def adam_step(param, grad, m, v, *, lr, beta1, beta2, eps, weight_decay, step, s
 
 def inc_counter(counter):
     L.check(L.load().srb_inc_counter(_ctx(counter), _p(counter), _stream()), "srb_inc_counter")
+
+
+# --------------------------------------------------------------------------------------------
+# layer chains (srb_conv_chain): many dependent 64-channel layers in one persistent launch
+# --------------------------------------------------------------------------------------------
+CHAIN_LAYER_BYTES = 9 * 64 * 64 * 2
+
+
+class FilterBank:
+    """Contiguous SRB_PACK_UMMA copies of the 3x3 64->64 filters a chain uses, one bank per pack
+    mode (forward / DGRAD).  Layer i is a slice of one uint8 tensor; the slices are registered in
+    the convs' PackedWeights caches so a PackTable refreshes them with every other packed copy."""
+
+    def __init__(self):
+        self.banks = {}
+
+    def get(self, convs, mode: int) -> torch.Tensor:
+        """convs: list of (weight parameter, PackedWeights).  Returns the bank, (re)packing stale layers."""
+        w0 = convs[0][0]
+        bank = self.banks.get(mode)
+        if bank is None or bank.device != w0.device or bank.numel() != len(convs) * CHAIN_LAYER_BYTES:
+            bank = torch.empty(len(convs) * CHAIN_LAYER_BYTES, dtype=torch.uint8, device=w0.device)
+            self.banks[mode] = bank
+        for i, (w, packs) in enumerate(convs):
+            assert tuple(w.shape) == (64, 64, 3, 3), "chain filter banks hold 3x3 64->64 convs only"
+            packs.get(w, L.PACK_UMMA, mode, 0, out=bank[i * CHAIN_LAYER_BYTES:(i + 1) * CHAIN_LAYER_BYTES])
+        return bank
+
+
+CHAIN_TRACE = None   # diagnostics: int64 device tensor that receives the event times of the next chain launches
+
+
+class Chain:
+    """Builder for one srb_conv_chain call.  Spaces are [slots, N, H, W, 64] bf16 tensors; `ref`
+    names a slot.  Ops run in order; an op may read what earlier ops wrote."""
+
+    def __init__(self, n: int, h: int, w: int, device):
+        self.n, self.h, self.w, self.device = n, h, w, device
+        self.spaces = [None] * 4
+        self.ops = []
+        self.keep = []
+
+    def space(self, index: int, t: torch.Tensor):
+        assert t.dim() == 5 and t.is_contiguous() and t.dtype == torch.bfloat16 and t.shape[4] == 64
+        assert tuple(t.shape[1:4]) == (self.n, self.h, self.w) and t.shape[0] < (1 << 14)
+        self.spaces[index] = t
+        return index
+
+    @staticmethod
+    def ref(space: int, slot: int) -> int:
+        return (space << 14) | slot
+
+    def _op(self, kind, x, y):
+        o = L.ChainOp()
+        o.kind, o.x, o.y, o.e, o.y2 = kind, x, y, L.CHAIN_NONE, L.CHAIN_NONE
+        o.scale, o.w_layer = 1.0, 0
+        self.ops.append(o)
+        return o
+
+    def _ptr(self, t):
+        if t is None:
+            return None
+        assert t.is_contiguous() and t.dtype == torch.float32 and t.device == self.device
+        self.keep.append(t)
+        return t.data_ptr()
+
+    def conv(self, x, y, w_layer, bias=None, *, relu=False, scale=1.0, res=None, mask=None, colsum=None, colsum_groups=1):
+        o = self._op(L.CHAIN_CONV, x, y)
+        o.w_layer, o.scale = w_layer, float(scale)
+        o.flags = (L.RELU if relu else 0) | (L.RESIDUAL if res is not None else 0) | (L.MASK if mask is not None else 0) | \
+                  (L.COLSUM if colsum is not None else 0)
+        if res is not None:
+            o.e = res
+        if mask is not None:
+            o.e = mask
+        o.bias = self._ptr(bias)
+        o.colsum = self._ptr(colsum)
+        o.colsum_groups = colsum_groups
+        return o
+
+    def conv_ca(self, x, t, out, skip, w_layer, bias, pool, w1, b1, w2, b2, s_out, y_out):
+        """RCAB second conv + CALayer + skip: t = conv(x)+bias -> slot t; out = t*gate + skip."""
+        o = self.conv(x, t, w_layer, bias, res=skip, colsum=pool, colsum_groups=self.n)
+        o.flags |= L.CHAIN_CA
+        o.y2 = out
+        o.ca_cr = w1.shape[0]
+        o.ca_w1, o.ca_b1, o.ca_w2, o.ca_b2 = self._ptr(w1), self._ptr(b1), self._ptr(w2), self._ptr(b2)
+        o.ca_s, o.ca_y = self._ptr(s_out), self._ptr(y_out)
+        return o
+
+    def ca_bwd(self, t, g, dt, w1, b1, w2, b2, s, y, dw1, db1, dw2, db2, scratch, colsum_dt=None):
+        o = self._op(L.CHAIN_CA_BWD, t, dt)
+        o.e = g
+        o.ca_cr = w1.shape[0]
+        o.ca_w1, o.ca_b1, o.ca_w2, o.ca_b2 = self._ptr(w1), self._ptr(b1), self._ptr(w2), self._ptr(b2)
+        o.ca_s, o.ca_y = self._ptr(s), self._ptr(y)
+        o.ca_dw1, o.ca_db1, o.ca_dw2, o.ca_db2 = self._ptr(dw1), self._ptr(db1), self._ptr(dw2), self._ptr(db2)
+        o.ca_scratch = self._ptr(scratch)
+        o.colsum = self._ptr(colsum_dt)
+        return o
+
+    def run(self, bank: torch.Tensor | None, trace: torch.Tensor | None = None):
+        """Launch; more than CHAIN_MAX_OPS ops are split into consecutive launches (stream order
+        carries the dependency across the split)."""
+        lib = L.load()
+        n_layers = bank.numel() // CHAIN_LAYER_BYTES if bank is not None else 0
+        for start in range(0, len(self.ops), L.CHAIN_MAX_OPS):
+            seg = self.ops[start:start + L.CHAIN_MAX_OPS]
+            arr = (L.ChainOp * len(seg))(*seg)
+            d = L.ChainDesc()
+            d.N, d.H, d.W, d.n_ops = self.n, self.h, self.w, len(seg)
+            d.ops = arr
+            for i, sp in enumerate(self.spaces):
+                d.space_base[i] = sp.data_ptr() if sp is not None else None
+                d.space_slots[i] = sp.shape[0] if sp is not None else 0
+            d.weights = bank.data_ptr() if bank is not None else None
+            d.n_layers = n_layers
+            counters = zeros_f32((len(seg) * 2 * self.n,), self.device)     # fp32 zero bits == int32 zero
+            self.keep.append(counters)
+            d.counters = counters.data_ptr()
+            if trace is None:
+                trace = CHAIN_TRACE
+            d.trace = trace.data_ptr() if trace is not None else None
+            L.check(lib.srb_conv_chain(C.c_void_p(L.ctx(self.device.index)), C.byref(d), _stream()), "srb_conv_chain")
+
+
+def chain_grid(device, n, h, w) -> int:
+    return int(L.load().srb_conv_chain_grid(C.c_void_p(L.ctx(device.index)), n, h, w))
