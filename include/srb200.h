@@ -164,7 +164,9 @@ int  srb_wgrad_uses_umma(const srb_wgrad_desc*);
  *   must be zero on entry.
  * counters: n_ops * 2 * N int32, zero on entry. */
 enum { SRB_CHAIN_CONV = 0, SRB_CHAIN_CA_BWD = 1 };
-enum { SRB_CHAIN_CA = 32 };            /* extra flag bit for SRB_CHAIN_CONV ops */
+enum { SRB_CHAIN_CA = 32,              /* extra flag bits for SRB_CHAIN_CONV ops */
+       SRB_CHAIN_CA_BWD_FUSED = 64 };  /* after y is stored, run CA_BWD on it: g = y, t = tile e2, dt -> y2,
+                                          column sums of dt -> colsum2 (saves a whole dependent op per RCAB) */
 #define SRB_CHAIN_NONE 0xFFFFu
 #define SRB_CHAIN_MAX_OPS 64
 
@@ -172,12 +174,15 @@ typedef struct srb_chain_op {
   int32_t  kind;
   uint32_t flags;
   uint16_t x, y, e, y2;     /* buffer references */
+  uint16_t e2, reserved0;   /* second operand tile (SRB_CHAIN_CA_BWD_FUSED: the saved t) */
   int32_t  w_layer;         /* index into the packed filter bank (CONV) */
   float    scale;
   int32_t  colsum_groups;   /* 1 -> colsum[64]; N -> colsum[N][64] (always N with SRB_CHAIN_CA) */
   int32_t  ca_cr;           /* hidden width of the CALayer (channel / reduction) */
+  int32_t  reserved1;
   const float* bias;        /* [64] or NULL */
   float*   colsum;
+  float*   colsum2;         /* SRB_CHAIN_CA_BWD_FUSED: [64] column sums of dt, or NULL */
   const float *ca_w1, *ca_b1, *ca_w2, *ca_b2;   /* conv_du.0 [Cr][64], [Cr]; conv_du.2 [64][Cr], [64] */
   float   *ca_s, *ca_y;                         /* [N][64]: written by SRB_CHAIN_CA, read by CA_BWD */
   float   *ca_dw1, *ca_db1, *ca_dw2, *ca_db2;   /* CA_BWD: accumulated */

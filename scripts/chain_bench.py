@@ -144,7 +144,7 @@ def main():
     tr.zero_()
     y.backward(gout)
     torch.cuda.synchronize()
-    analyse(tr[:grid * 2 * (3 * nb + 1) * 8], 3 * nb + 1, ["tail_dgrad"] + ["ca_bwd", "dgrad2+mask", "dgrad1+res"] * nb, "group backward")
+    analyse(tr[:grid * 2 * (2 * nb + 1) * 8], 2 * nb + 1, ["tail_dgrad"] + ["dgrad2+mask", "dgrad1+cabwd"] * nb, "group backward")
     ops.CHAIN_TRACE = None
 
 

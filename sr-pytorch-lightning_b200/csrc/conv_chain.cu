@@ -20,6 +20,8 @@
 // acquires counters[op-1][0][n] == tiles_per_sample before it requests its input window.  All CTAs
 // walk (op, tile) in the same order and only wait on strictly earlier ops, so there is no cycle;
 // the grid is <= the SM count with one CTA per SM, i.e. all CTAs are co-resident.
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -33,10 +35,12 @@ constexpr uint32_t kWinStride = 23u * 1024u;
 constexpr uint32_t kSlabBytes = 3u * 64u * 128u; // one kw slab: [kh][cout][cin]
 constexpr uint32_t kWBytes = 3u * kSlabBytes;    // 73728
 constexpr uint32_t kTileBytes = 128u * 128u;
-constexpr uint32_t kChainStride = kWinStride + 2u * kTileBytes;   // window | staging | operand tile
+constexpr uint32_t kChainStride = kWinStride + 3u * kTileBytes;   // window | staging | operand tile | 2nd operand tile
 constexpr uint32_t kSmemBytes = kWBytes + 2u * kChainStride + 1024u;
 constexpr uint32_t kTmemCols = 128;
 constexpr int kMaxCr = 16;
+constexpr uint32_t kScaled = 1u << 16;    // epilogue specialisation keys: scale != 1 / no specialisation
+constexpr uint32_t kGeneric = 1u << 17;
 
 struct ChainMaps {
   CUtensorMap win[4];    // 5-D (c, w, h, n, slot), box 64 x 10 x 18
@@ -151,9 +155,10 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t w_full[3], w_empty[3];
-  __shared__ uint64_t a_full[2], a_empty[2], e_full[2], e_empty[2], acc_full[2], acc_empty[2];
+  __shared__ uint64_t a_full[2], a_empty[2], e_full[2], e_empty[2], e2_full[2], e2_empty[2], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float bias_s[2][64];
+  __shared__ float colsum_s[2][4][64];
   __shared__ float ca_s[2][64], ca_y[2][64], ca_du[2][64], ca_ds[2][64], ca_z[2][kMaxCr], ca_dv[2][kMaxCr];
 
   const int warp = threadIdx.x >> 5;
@@ -174,6 +179,8 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
       ptx::mbar_init(&a_empty[c], 1);
       ptx::mbar_init(&e_full[c], 1);
       ptx::mbar_init(&e_empty[c], 1);
+      ptx::mbar_init(&e2_full[c], 1);
+      ptx::mbar_init(&e2_empty[c], 1);
       ptx::mbar_init(&acc_full[c], 1);
       ptx::mbar_init(&acc_empty[c], 1);
     }
@@ -200,7 +207,8 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
       const int c = warp;
       const uint32_t win = base + kWBytes + (uint32_t)c * kChainStride;
       const uint32_t ebuf = win + kWinStride + kTileBytes;
-      uint32_t a_k = 0, e_k = 0;
+      const uint32_t e2buf = ebuf + kTileBytes;
+      uint32_t a_k = 0, e_k = 0, e2_k = 0;
       for (int op = 0; op < p.n_ops; ++op) {
         const srb_chain_op& o = p.ops[op];
         for (int j = c; j < my_tiles; j += 2) {
@@ -227,6 +235,12 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
             ptx::mbar_arrive_expect_tx(&e_full[c], kTileBytes);
             tma_load_5d(ebuf, &maps.tile[ref_space(o.e)], &e_full[c], 0, w0, h0, n, ref_slot(o.e));
             ++e_k;
+          }
+          if (o.e2 != SRB_CHAIN_NONE) {
+            ptx::mbar_wait(&e2_empty[c], (e2_k & 1u) ^ 1u);
+            ptx::mbar_arrive_expect_tx(&e2_full[c], kTileBytes);
+            tma_load_5d(e2buf, &maps.tile[ref_space(o.e2)], &e2_full[c], 0, w0, h0, n, ref_slot(o.e2));
+            ++e2_k;
           }
         }
       }
@@ -314,8 +328,10 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
     const uint32_t orow = stg + (uint32_t)row * 128u;
     const uint32_t erow = ebuf + (uint32_t)row * 128u;
     const uint32_t trow = win + (uint32_t)row * 128u;   // CA_BWD: the t tile lands in the window buffer
+    const uint32_t e2buf = ebuf + kTileBytes;
+    const uint32_t e2row = e2buf + (uint32_t)row * 128u;
     const float inv_hw = 1.f / (float)(p.H * p.W);
-    uint32_t a_k = 0, e_k = 0, acc_k = 0;
+    uint32_t a_k = 0, e_k = 0, e2_k = 0, acc_k = 0;
 
     for (int op = 0; op < p.n_ops; ++op) {
       const srb_chain_op& o = p.ops[op];
@@ -330,197 +346,17 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
         int* cnt_done = p.counters + ((size_t)op * 2) * N + n;
         int* cnt_part = p.counters + ((size_t)op * 2 + 1) * N + n;
 
-        if (o.kind == SRB_CHAIN_CONV) {
-          const bool has_e = o.e != SRB_CHAIN_NONE;
-          const bool ca = (flags & SRB_CHAIN_CA) != 0;
-          // the bias of this op is cold in L1 (every op has its own): fetch it into shared memory
-          // while the MMAs run instead of stalling each 32-column chunk on an L2 round trip
-          if (row < 64) bias_s[c][row] = o.bias ? __ldg(o.bias + row) : 0.f;
-          ptx::named_bar_sync(bar_id, 128);
-          ptx::mbar_wait(&acc_full[c], acc_k & 1u);
-          ptx::tc_fence_after();
-          if (store_thread) CH_TRACE(c, op, TR_ACC);
-          if (has_e) ptx::mbar_wait(&e_full[c], e_k & 1u);
-          uint32_t acc2[2][32];
-          ptx::tmem_ld_32x32b_x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 64), acc2[0]);
-          ptx::tmem_ld_32x32b_x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 64 + 32), acc2[1]);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int hc = 0; hc < 2; ++hc) {
-            const int c0 = hc * 32;
-            float v[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc2[hc][i]);
-            if (o.bias) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 b = *reinterpret_cast<const float4*>(&bias_s[c][c0 + i]);
-                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-              }
-            }
-            if (flags & SRB_RELU) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-            }
-            if (o.scale != 1.f) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] *= o.scale;
-            }
-            if (flags & SRB_MASK) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const uint4 m = ptx::lds128(erow + ((((uint32_t)(c0 >> 3) + g) ^ sw) << 4));
-                const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = unpack_bf16x2(mw[e]);
-                  if (!(f.x > 0.f)) v[g * 8 + e * 2] = 0.f;
-                  if (!(f.y > 0.f)) v[g * 8 + e * 2 + 1] = 0.f;
-                }
-              }
-            }
-            if ((flags & SRB_RESIDUAL) && !ca) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const uint4 m = ptx::lds128(erow + ((((uint32_t)(c0 >> 3) + g) ^ sw) << 4));
-                const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = unpack_bf16x2(mw[e]);
-                  v[g * 8 + e * 2] += f.x;
-                  v[g * 8 + e * 2 + 1] += f.y;
-                }
-              }
-            }
-            uint32_t packed[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) packed[i] = valid ? pack_bf16x2(v[2 * i], v[2 * i + 1]) : 0u;
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              ptx::sts128(orow + ((((uint32_t)(c0 >> 3) + g) ^ sw) << 4),
-                          make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]));
-            if (flags & SRB_COLSUM) {
-              float s[32];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float2 f = unpack_bf16x2(packed[i]);
-                s[2 * i] = f.x;
-                s[2 * i + 1] = f.y;
-              }
-              const float tot = warp_colsum32(s, lane);
-              const int g = o.colsum_groups > 1 ? n : 0;
-              atomicAdd(o.colsum + (int64_t)g * 64 + c0 + lane, tot);
-            }
-          }
-          ptx::tc_fence_before();
-          ptx::fence_proxy_async_smem();
-          ptx::named_bar_sync(bar_id, 128);
-          if (!ca) {
-            if (store_thread) {
-              ptx::mbar_arrive(&acc_empty[c]);
-              if (has_e) ptx::mbar_arrive(&e_empty[c]);
-              tma_store_5d(&maps.tile[ref_space(o.y)], stg, 0, w0, h0, n, ref_slot(o.y));
-              ptx::bulk_commit_group();
-              CH_TRACE(c, op, TR_STAGED);
-            }
-          } else {
-            // ---- CALayer gate + RCAB skip (rcan.py:10-29,54) on the tile still in the staging buffer ----
-            // The pooled-sum contributions of all 128 threads precede the barrier above; the release
-            // below (one thread, gpu scope) is cumulative over them — the cutlass::Barrier::arrive_inc
-            // pattern — so no per-thread fence is needed.  It is issued BEFORE the store of t so that it
-            // does not wait behind it.
-            if (store_thread) {
-              ptx::mbar_arrive(&acc_empty[c]);
-              red_release_gpu(cnt_part, 1);
-              tma_store_5d(&maps.tile[ref_space(o.y)], stg, 0, w0, h0, n, ref_slot(o.y));
-              ptx::bulk_commit_group();
-              CH_TRACE(c, op, TR_STAGED);
-            }
-            // gate operands do not depend on the pool: fetch them (cold in L1 — every acquire poll
-            // invalidates it) while the other tiles of the sample arrive
-            float w1a[2] = {0.f, 0.f}, w1b[2] = {0.f, 0.f}, b1v[2] = {0.f, 0.f};
-            {
-              int u = 0;
-              for (int jj = q; jj < Cr && u < 2; jj += 4, ++u) {
-                w1a[u] = __ldg(o.ca_w1 + jj * 64 + lane);
-                w1b[u] = __ldg(o.ca_w1 + jj * 64 + lane + 32);
-                b1v[u] = __ldg(o.ca_b1 + jj);
-              }
-            }
-            float w2r[4] = {0.f, 0.f, 0.f, 0.f}, b2v = 0.f;
-            if (row < 64) {
-              b2v = __ldg(o.ca_b2 + row);
-              for (int jj = 0; jj < Cr && jj < 4; ++jj) w2r[jj] = __ldg(o.ca_w2 + row * Cr + jj);
-            }
-            if (store_thread) {
-              wait_counter(cnt_part, p.tiles_per_sample);
-              CH_TRACE(c, op, TR_POOL);
-            }
-            ptx::named_bar_sync(bar_id, 128);
-            if (row < 64) ca_s[c][row] = __ldcg(o.colsum + (int64_t)n * 64 + row) * inv_hw;
-            ptx::named_bar_sync(bar_id, 128);
-            {
-              int u = 0;
-              for (int jj = q; jj < Cr; jj += 4, ++u) {
-                float a = (u < 2 ? w1a[u] : __ldg(o.ca_w1 + jj * 64 + lane)) * ca_s[c][lane] +
-                          (u < 2 ? w1b[u] : __ldg(o.ca_w1 + jj * 64 + lane + 32)) * ca_s[c][lane + 32];
-                a = warp_sum(a);
-                if (lane == 0) ca_z[c][jj] = fmaxf(a + (u < 2 ? b1v[u] : __ldg(o.ca_b1 + jj)), 0.f);
-              }
-            }
-            ptx::named_bar_sync(bar_id, 128);
-            if (row < 64) {
-              float u = b2v;
-              for (int jj = 0; jj < Cr; ++jj) u += (jj < 4 ? w2r[jj] : __ldg(o.ca_w2 + row * Cr + jj)) * ca_z[c][jj];
-              const float yv = 1.f / (1.f + expf(-u));
-              ca_y[c][row] = yv;
-              if (r == 0) {
-                o.ca_s[(int64_t)n * 64 + row] = ca_s[c][row];
-                o.ca_y[(int64_t)n * 64 + row] = yv;
-              }
-            }
-            ptx::named_bar_sync(bar_id, 128);
-            // out = t * gate + skip, written over the skip tile (dead afterwards): the staging buffer may
-            // still be read by the store of t
-#pragma unroll 1
-            for (int c0 = 0; c0 < 64; c0 += 32) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const uint32_t off = (((uint32_t)(c0 >> 3) + g) ^ sw) << 4;
-                const uint4 tv = ptx::lds128(orow + off);
-                const uint4 xv = ptx::lds128(erow + off);
-                const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w}, xw[4] = {xv.x, xv.y, xv.z, xv.w};
-                uint32_t pk[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 ft = unpack_bf16x2(tw[e]), fx = unpack_bf16x2(xw[e]);
-                  const int ch = c0 + g * 8 + e * 2;
-                  pk[e] = pack_bf16x2(fmaf(ft.x, ca_y[c][ch], fx.x), fmaf(ft.y, ca_y[c][ch + 1], fx.y));
-                }
-                ptx::sts128(erow + off, make_uint4(pk[0], pk[1], pk[2], pk[3]));
-              }
-            }
-            ptx::fence_proxy_async_smem();
-            ptx::named_bar_sync(bar_id, 128);
-            if (store_thread) {
-              tma_store_5d(&maps.tile[ref_space(o.y2)], ebuf, 0, w0, h0, n, ref_slot(o.y2));
-              ptx::bulk_commit_group();
-            }
-          }
-          ++acc_k;
-          if (has_e) ++e_k;
-        } else {
-          // ---- CALayer + skip backward (tile op, no MMA): x = t tile (window buffer), e = g tile ----
-          ptx::mbar_wait(&a_full[c], a_k & 1u);
-          ptx::mbar_wait(&e_full[c], e_k & 1u);
+        // CALayer + skip backward on one tile (rcan.py:10-29,54): g_row / t_row = this thread's 128-byte rows
+        // of dL/dout and of the saved pre-attention tensor; dt = g*gate + ds/HW is written to out_row.
+        auto ca_bwd_tile = [&](const uint32_t g_row, const uint32_t t_row, const uint32_t out_row, float* colsum_dt) {
 #pragma unroll 1
           for (int c0 = 0; c0 < 64; c0 += 32) {
             float s[32];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               const uint32_t off = (((uint32_t)(c0 >> 3) + g) ^ sw) << 4;
-              const uint4 tv = ptx::lds128(trow + off);
-              const uint4 gv = ptx::lds128(erow + off);
+              const uint4 tv = ptx::lds128(t_row + off);
+              const uint4 gv = ptx::lds128(g_row + off);
               const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -529,8 +365,12 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
                 s[g * 8 + e * 2 + 1] = ft.y * fg.y;
               }
             }
-            const float tot = warp_colsum32(s, lane);      // out-of-image rows are zero-filled by TMA
-            atomicAdd(o.ca_scratch + (int64_t)n * 64 + c0 + lane, tot);
+            colsum_s[c][q][c0 + lane] = warp_colsum32(s, lane);      // out-of-image rows are zero-filled by TMA
+          }
+          ptx::named_bar_sync(bar_id, 128);
+          if (row < 64) {
+            const float tot = (colsum_s[c][0][row] + colsum_s[c][1][row]) + (colsum_s[c][2][row] + colsum_s[c][3][row]);
+            atomicAdd(o.ca_scratch + (int64_t)n * 64 + row, tot);
           }
           ptx::named_bar_sync(bar_id, 128);      // all partial sums issued; the release below is cumulative over them
           if (store_thread) red_release_gpu(cnt_part, 1);
@@ -627,7 +467,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               const uint32_t off = (((uint32_t)(c0 >> 3) + g) ^ sw) << 4;
-              const uint4 gv = ptx::lds128(erow + off);
+              const uint4 gv = ptx::lds128(g_row + off);
               const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -637,9 +477,9 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
                                                         fmaf(fg.y, ca_y[c][ch + 1], ca_ds[c][ch + 1]))
                                           : 0u;
               }
-              ptx::sts128(orow + off, make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]));
+              ptx::sts128(out_row + off, make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]));
             }
-            if (o.colsum) {
+            if (colsum_dt) {
               float s[32];
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
@@ -647,10 +487,239 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
                 s[2 * i] = f.x;
                 s[2 * i + 1] = f.y;
               }
-              const float tot = warp_colsum32(s, lane);
-              atomicAdd(o.colsum + c0 + lane, tot);
+              colsum_s[c][q][c0 + lane] = warp_colsum32(s, lane);
             }
           }
+          if (colsum_dt) {
+            ptx::named_bar_sync(bar_id, 128);
+            if (row < 64) {
+              const float tot = (colsum_s[c][0][row] + colsum_s[c][1][row]) + (colsum_s[c][2][row] + colsum_s[c][3][row]);
+              atomicAdd(colsum_dt + row, tot);
+            }
+          }
+        };
+
+        if (o.kind == SRB_CHAIN_CONV) {
+          const bool has_e = o.e != SRB_CHAIN_NONE;
+          const bool ca = (flags & SRB_CHAIN_CA) != 0;
+          // the bias of this op is cold in L1 (every op has its own): fetch it into shared memory
+          // while the MMAs run instead of stalling each 32-column chunk on an L2 round trip
+          if (row < 64) bias_s[c][row] = o.bias ? __ldg(o.bias + row) : 0.f;
+          ptx::named_bar_sync(bar_id, 128);
+          ptx::mbar_wait(&acc_full[c], acc_k & 1u);
+          ptx::tc_fence_after();
+          if (store_thread) CH_TRACE(c, op, TR_ACC);
+          if (has_e) ptx::mbar_wait(&e_full[c], e_k & 1u);
+          // Epilogue arithmetic, specialised at compile time on the op's flag combination: the block runs
+          // once per tile from a cold instruction cache, and every skipped `if (flags & ...)` section was
+          // a taken branch plus an instruction refetch (ncu: no_inst + branch_resolving = half the stalls).
+          auto epilogue = [&](auto FC) {
+            constexpr uint32_t F = decltype(FC)::value;
+            uint32_t acc2[2][32];
+            ptx::tmem_ld_32x32b_x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 64), acc2[0]);
+            ptx::tmem_ld_32x32b_x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 64 + 32), acc2[1]);
+            ptx::tmem_ld_wait();
+            const uint32_t fl = (F == kGeneric) ? flags : F;
+            const float scale = o.scale;
+#pragma unroll
+            for (int hc = 0; hc < 2; ++hc) {
+              const int c0 = hc * 32;
+              float v[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc2[hc][i]);
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {     // bias_s holds zeros when the op has no bias
+                const float4 bq = *reinterpret_cast<const float4*>(&bias_s[c][c0 + i]);
+                v[i] += bq.x; v[i + 1] += bq.y; v[i + 2] += bq.z; v[i + 3] += bq.w;
+              }
+              if (fl & SRB_RELU) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+              }
+              if ((F == kGeneric || (F & kScaled)) && scale != 1.f) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] *= scale;
+              }
+              if (fl & SRB_MASK) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  const uint4 m = ptx::lds128(erow + ((((uint32_t)(c0 >> 3) + g) ^ sw) << 4));
+                  const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = unpack_bf16x2(mw[e]);
+                    if (!(f.x > 0.f)) v[g * 8 + e * 2] = 0.f;
+                    if (!(f.y > 0.f)) v[g * 8 + e * 2 + 1] = 0.f;
+                  }
+                }
+              }
+              if ((fl & SRB_RESIDUAL) && !(fl & SRB_CHAIN_CA)) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  const uint4 m = ptx::lds128(erow + ((((uint32_t)(c0 >> 3) + g) ^ sw) << 4));
+                  const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = unpack_bf16x2(mw[e]);
+                    v[g * 8 + e * 2] += f.x;
+                    v[g * 8 + e * 2 + 1] += f.y;
+                  }
+                }
+              }
+              uint32_t packed[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) packed[i] = valid ? pack_bf16x2(v[2 * i], v[2 * i + 1]) : 0u;
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                ptx::sts128(orow + ((((uint32_t)(c0 >> 3) + g) ^ sw) << 4),
+                            make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]));
+              if (fl & SRB_COLSUM) {
+                // sums of the STORED (bf16-rounded) values over this warp's 32 pixels; the four warps'
+                // partial sums meet in shared memory so that a tile issues 64 atomics, not 256
+                float s[32];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const float2 f = unpack_bf16x2(packed[i]);
+                  s[2 * i] = f.x;
+                  s[2 * i + 1] = f.y;
+                }
+                colsum_s[c][q][c0 + lane] = warp_colsum32(s, lane);
+              }
+            }
+          };
+          switch ((flags & 47u) | (o.scale != 1.f ? kScaled : 0u)) {
+            case SRB_RELU: epilogue(std::integral_constant<uint32_t, SRB_RELU>{}); break;
+            case SRB_RESIDUAL: epilogue(std::integral_constant<uint32_t, SRB_RESIDUAL>{}); break;
+            case SRB_RESIDUAL | kScaled: epilogue(std::integral_constant<uint32_t, SRB_RESIDUAL | kScaled>{}); break;
+            case SRB_MASK | SRB_COLSUM: epilogue(std::integral_constant<uint32_t, SRB_MASK | SRB_COLSUM>{}); break;
+            case SRB_MASK | SRB_COLSUM | kScaled: epilogue(std::integral_constant<uint32_t, SRB_MASK | SRB_COLSUM | kScaled>{}); break;
+            case SRB_RESIDUAL | SRB_COLSUM | SRB_CHAIN_CA:
+              epilogue(std::integral_constant<uint32_t, SRB_RESIDUAL | SRB_COLSUM | SRB_CHAIN_CA>{});
+              break;
+            case 0: epilogue(std::integral_constant<uint32_t, 0>{}); break;
+            default: epilogue(std::integral_constant<uint32_t, kGeneric>{}); break;
+          }
+          ptx::tc_fence_before();
+          ptx::fence_proxy_async_smem();
+          ptx::named_bar_sync(bar_id, 128);
+          if ((flags & SRB_COLSUM) && row < 64) {
+            const float tot = (colsum_s[c][0][row] + colsum_s[c][1][row]) + (colsum_s[c][2][row] + colsum_s[c][3][row]);
+            atomicAdd(o.colsum + (int64_t)(o.colsum_groups > 1 ? n : 0) * 64 + row, tot);
+          }
+          if (ca) ptx::named_bar_sync(bar_id, 128);   // pooled-sum contributions precede the cumulative release below
+          if (!ca) {
+            if (store_thread) {
+              ptx::mbar_arrive(&acc_empty[c]);
+              if (has_e) ptx::mbar_arrive(&e_empty[c]);
+              tma_store_5d(&maps.tile[ref_space(o.y)], stg, 0, w0, h0, n, ref_slot(o.y));
+              ptx::bulk_commit_group();
+              CH_TRACE(c, op, TR_STAGED);
+            }
+            if (flags & SRB_CHAIN_CA_BWD_FUSED) {
+              // y (just staged, bf16) is dL/dout of the previous RCAB: run its CALayer backward here
+              // instead of as a dependent op.  The staging buffer is only READ (the store of y may
+              // still be reading it too); dt overwrites the t tile and is stored from there.
+              ptx::mbar_wait(&e2_full[c], e2_k & 1u);
+              ca_bwd_tile(orow, e2row, e2row, o.colsum2);
+              ptx::fence_proxy_async_smem();
+              ptx::named_bar_sync(bar_id, 128);
+              if (store_thread) {
+                tma_store_5d(&maps.tile[ref_space(o.y2)], e2buf, 0, w0, h0, n, ref_slot(o.y2));
+                ptx::bulk_commit_group();
+              }
+              ++e2_k;
+            }
+          } else {
+            // ---- CALayer gate + RCAB skip (rcan.py:10-29,54) on the tile still in the staging buffer ----
+            // The pooled-sum contributions of all 128 threads precede the barrier above; the release
+            // below (one thread, gpu scope) is cumulative over them — the cutlass::Barrier::arrive_inc
+            // pattern — so no per-thread fence is needed.  It is issued BEFORE the store of t so that it
+            // does not wait behind it.
+            if (store_thread) {
+              ptx::mbar_arrive(&acc_empty[c]);
+              red_release_gpu(cnt_part, 1);
+              tma_store_5d(&maps.tile[ref_space(o.y)], stg, 0, w0, h0, n, ref_slot(o.y));
+              ptx::bulk_commit_group();
+              CH_TRACE(c, op, TR_STAGED);
+            }
+            // gate operands do not depend on the pool: fetch them (cold in L1 — every acquire poll
+            // invalidates it) while the other tiles of the sample arrive
+            float w1a[2] = {0.f, 0.f}, w1b[2] = {0.f, 0.f}, b1v[2] = {0.f, 0.f};
+            {
+              int u = 0;
+              for (int jj = q; jj < Cr && u < 2; jj += 4, ++u) {
+                w1a[u] = __ldg(o.ca_w1 + jj * 64 + lane);
+                w1b[u] = __ldg(o.ca_w1 + jj * 64 + lane + 32);
+                b1v[u] = __ldg(o.ca_b1 + jj);
+              }
+            }
+            float w2r[4] = {0.f, 0.f, 0.f, 0.f}, b2v = 0.f;
+            if (row < 64) {
+              b2v = __ldg(o.ca_b2 + row);
+              for (int jj = 0; jj < Cr && jj < 4; ++jj) w2r[jj] = __ldg(o.ca_w2 + row * Cr + jj);
+            }
+            if (store_thread) {
+              wait_counter(cnt_part, p.tiles_per_sample);
+              CH_TRACE(c, op, TR_POOL);
+            }
+            ptx::named_bar_sync(bar_id, 128);
+            if (row < 64) ca_s[c][row] = __ldcg(o.colsum + (int64_t)n * 64 + row) * inv_hw;
+            ptx::named_bar_sync(bar_id, 128);
+            {
+              int u = 0;
+              for (int jj = q; jj < Cr; jj += 4, ++u) {
+                float a = (u < 2 ? w1a[u] : __ldg(o.ca_w1 + jj * 64 + lane)) * ca_s[c][lane] +
+                          (u < 2 ? w1b[u] : __ldg(o.ca_w1 + jj * 64 + lane + 32)) * ca_s[c][lane + 32];
+                a = warp_sum(a);
+                if (lane == 0) ca_z[c][jj] = fmaxf(a + (u < 2 ? b1v[u] : __ldg(o.ca_b1 + jj)), 0.f);
+              }
+            }
+            ptx::named_bar_sync(bar_id, 128);
+            if (row < 64) {
+              float u = b2v;
+              for (int jj = 0; jj < Cr; ++jj) u += (jj < 4 ? w2r[jj] : __ldg(o.ca_w2 + row * Cr + jj)) * ca_z[c][jj];
+              const float yv = 1.f / (1.f + expf(-u));
+              ca_y[c][row] = yv;
+              if (r == 0) {
+                o.ca_s[(int64_t)n * 64 + row] = ca_s[c][row];
+                o.ca_y[(int64_t)n * 64 + row] = yv;
+              }
+            }
+            ptx::named_bar_sync(bar_id, 128);
+            // out = t * gate + skip, written over the skip tile (dead afterwards): the staging buffer may
+            // still be read by the store of t
+#pragma unroll 1
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint32_t off = (((uint32_t)(c0 >> 3) + g) ^ sw) << 4;
+                const uint4 tv = ptx::lds128(orow + off);
+                const uint4 xv = ptx::lds128(erow + off);
+                const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w}, xw[4] = {xv.x, xv.y, xv.z, xv.w};
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 ft = unpack_bf16x2(tw[e]), fx = unpack_bf16x2(xw[e]);
+                  const int ch = c0 + g * 8 + e * 2;
+                  pk[e] = pack_bf16x2(fmaf(ft.x, ca_y[c][ch], fx.x), fmaf(ft.y, ca_y[c][ch + 1], fx.y));
+                }
+                ptx::sts128(erow + off, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+              }
+            }
+            ptx::fence_proxy_async_smem();
+            ptx::named_bar_sync(bar_id, 128);
+            if (store_thread) {
+              tma_store_5d(&maps.tile[ref_space(o.y2)], ebuf, 0, w0, h0, n, ref_slot(o.y2));
+              ptx::bulk_commit_group();
+            }
+          }
+          ++acc_k;
+          if (has_e) ++e_k;
+        } else {
+          // ---- CALayer + skip backward (tile op, no MMA): x = t tile (window buffer), e = g tile ----
+          ptx::mbar_wait(&a_full[c], a_k & 1u);
+          ptx::mbar_wait(&e_full[c], e_k & 1u);
+          ca_bwd_tile(erow, trow, orow, o.colsum);
           ptx::fence_proxy_async_smem();
           ptx::named_bar_sync(bar_id, 128);
           if (store_thread) {
@@ -666,6 +735,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
         if (store_thread) {
           ptx::bulk_wait_group<0>();
           if (o.kind == SRB_CHAIN_CONV && (flags & SRB_CHAIN_CA)) ptx::mbar_arrive(&e_empty[c]);   // out was staged in it
+          if (o.kind == SRB_CHAIN_CONV && (flags & SRB_CHAIN_CA_BWD_FUSED)) ptx::mbar_arrive(&e2_empty[c]);   // so was dt
           CH_TRACE(c, op, TR_STORED);
           fence_proxy_async_all();            // async-proxy (TMA) writes ordered before the generic-proxy release
           red_release_gpu(cnt_done, 1);       // release.gpu: no separate __threadfence (a MEMBAR.SC costs ~1 us)
@@ -791,6 +861,18 @@ extern "C" int srb_conv_chain(srb_ctx* ctx, const srb_chain_desc* d, void* strea
       SRB_REQUIRE((m || r) || o.e == SRB_CHAIN_NONE, "srb_conv_chain: op %d has an operand tile but no MASK/RESIDUAL flag", i);
       SRB_REQUIRE(!(o.flags & SRB_COLSUM) || (o.colsum && (o.colsum_groups == 1 || o.colsum_groups == d->N)),
                   "srb_conv_chain: op %d: COLSUM needs a pointer and groups in {1, N}", i);
+      SRB_REQUIRE((o.e2 != SRB_CHAIN_NONE) == ((o.flags & SRB_CHAIN_CA_BWD_FUSED) != 0),
+                  "srb_conv_chain: op %d: a second operand tile goes with CA_BWD_FUSED and only with it", i);
+      if (o.flags & SRB_CHAIN_CA_BWD_FUSED) {
+        SRB_REQUIRE(sample_sync_ok, "srb_conv_chain: op %d: CA ops need tiles_per_sample (%d) <= 2 x grid (%d); use srb_ca_bwd", i,
+                    p.tiles_per_sample, grid_for_check);
+        SRB_REQUIRE(!(o.flags & SRB_CHAIN_CA), "srb_conv_chain: op %d: CA and CA_BWD_FUSED are exclusive", i);
+        if ((rc = check_ref(o.e2, true, "saved t", i))) return rc;
+        if ((rc = check_ref(o.y2, true, "dt output", i))) return rc;
+        SRB_REQUIRE(o.ca_w1 && o.ca_b1 && o.ca_w2 && o.ca_b2 && o.ca_s && o.ca_y && o.ca_dw1 && o.ca_db1 && o.ca_dw2 &&
+                        o.ca_db2 && o.ca_scratch && o.ca_cr >= 1 && o.ca_cr <= kMaxCr,
+                    "srb_conv_chain: op %d: CA_BWD_FUSED pointers missing or Cr outside [1,%d]", i, kMaxCr);
+      }
       if (o.flags & SRB_CHAIN_CA) {
         SRB_REQUIRE(sample_sync_ok, "srb_conv_chain: op %d: CA ops need tiles_per_sample (%d) <= 2 x grid (%d); use srb_ca_fwd",
                     i, p.tiles_per_sample, grid_for_check);
@@ -801,6 +883,7 @@ extern "C" int srb_conv_chain(srb_ctx* ctx, const srb_chain_desc* d, void* strea
         if ((rc = check_ref(o.y2, true, "CA output", i))) return rc;
       }
     } else if (o.kind == SRB_CHAIN_CA_BWD) {
+      SRB_REQUIRE(o.e2 == SRB_CHAIN_NONE, "srb_conv_chain: op %d: CA_BWD takes no second operand tile", i);
       SRB_REQUIRE(sample_sync_ok, "srb_conv_chain: op %d: CA ops need tiles_per_sample (%d) <= 2 x grid (%d); use srb_ca_bwd", i,
                   p.tiles_per_sample, grid_for_check);
       if ((rc = check_ref(o.e, true, "gradient", i))) return rc;

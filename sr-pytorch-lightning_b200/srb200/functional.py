@@ -286,24 +286,28 @@ class RCANGroupFn(Function):
         ref = ops.Chain.ref
         grads = [None] * len(params)
         wq = []   # (x tensor, gy tensor, weight index, bias index or None)
-        # group tail conv: out = conv(last) + x
-        ch.conv(ref(2, 0), ref(0, 3 * nb), 2 * nb)
-        wq.append((A[3 * nb - 1], g, len(params) - 2, len(params) - 1))
-        gref = ref(0, 3 * nb)
-        for b in range(nb - 1, -1, -1):
+        def ca_args(b):
+            """Fused CALayer backward of RCAB b: consumes the dL/dout the current op produces."""
             w1, b1, w2, b2, cw1, cb1, cw2, cb2 = params[8 * b:8 * b + 8]
-            db1, grads[8 * b + 1] = _zeroed_grad_target(b1)
             db2, grads[8 * b + 3] = _zeroed_grad_target(b2)
             dcw1, grads[8 * b + 4] = _zeroed_grad_target(cw1)
             dcb1, grads[8 * b + 5] = _zeroed_grad_target(cb1)
             dcw2, grads[8 * b + 6] = _zeroed_grad_target(cw2)
             dcb2, grads[8 * b + 7] = _zeroed_grad_target(cb2)
             cr = cw1.shape[0]
-            ch.ca_bwd(ref(1, 3 * b + 1), gref, ref(0, 3 * b), cw1.detach().reshape(cr, 64), cb1.detach(),
-                      cw2.detach().reshape(64, cr), cb2.detach(), s_all[b], y_all[b], dcw1.view(cr, 64), dcb1,
-                      dcw2.view(64, cr), dcb2, scratch[b], colsum_dt=db2)
+            return dict(t=ref(1, 3 * b + 1), dt=ref(0, 3 * b), w1=cw1.detach().reshape(cr, 64), b1=cb1.detach(),
+                        w2=cw2.detach().reshape(64, cr), b2=cb2.detach(), s=s_all[b], y=y_all[b], dw1=dcw1.view(cr, 64),
+                        db1=dcb1, dw2=dcw2.view(64, cr), db2=dcb2, scratch=scratch[b], colsum_dt=db2)
+
+        # group tail conv: out = conv(last) + x; its input gradient is dL/dout of the last RCAB
+        ch.conv(ref(2, 0), ref(0, 3 * nb), 2 * nb, ca_bwd=ca_args(nb - 1))
+        wq.append((A[3 * nb - 1], g, len(params) - 2, len(params) - 1))
+        gref = ref(0, 3 * nb)
+        for b in range(nb - 1, -1, -1):
+            b1 = params[8 * b + 1]
+            db1, grads[8 * b + 1] = _zeroed_grad_target(b1)
             ch.conv(ref(0, 3 * b), ref(0, 3 * b + 1), 2 * b + 1, mask=ref(1, 3 * b), colsum=db1, colsum_groups=1)
-            ch.conv(ref(0, 3 * b + 1), ref(0, 3 * b + 2), 2 * b, res=gref)
+            ch.conv(ref(0, 3 * b + 1), ref(0, 3 * b + 2), 2 * b, res=gref, ca_bwd=ca_args(b - 1) if b > 0 else None)
             wq.append((A[3 * b], B[3 * b], 8 * b + 2, None))
             wq.append((A[3 * b - 1] if b > 0 else x, B[3 * b + 1], 8 * b, None))
             gref = ref(0, 3 * b + 2)

@@ -501,7 +501,7 @@ class Chain:
 
     def _op(self, kind, x, y):
         o = L.ChainOp()
-        o.kind, o.x, o.y, o.e, o.y2 = kind, x, y, L.CHAIN_NONE, L.CHAIN_NONE
+        o.kind, o.x, o.y, o.e, o.y2, o.e2 = kind, x, y, L.CHAIN_NONE, L.CHAIN_NONE, L.CHAIN_NONE
         o.scale, o.w_layer = 1.0, 0
         self.ops.append(o)
         return o
@@ -513,8 +513,13 @@ class Chain:
         self.keep.append(t)
         return t.data_ptr()
 
-    def conv(self, x, y, w_layer, bias=None, *, relu=False, scale=1.0, res=None, mask=None, colsum=None, colsum_groups=1):
+    def conv(self, x, y, w_layer, bias=None, *, relu=False, scale=1.0, res=None, mask=None, colsum=None, colsum_groups=1,
+             ca_bwd=None):
+        """ca_bwd: dict(t=ref, dt=ref, w1, b1, w2, b2, s, y, dw1, db1, dw2, db2, scratch, colsum_dt) — fuse the
+        CALayer backward of the block whose dL/dout this conv produces (SRB_CHAIN_CA_BWD_FUSED)."""
         o = self._op(L.CHAIN_CONV, x, y)
+        if ca_bwd is not None:
+            self._fill_ca_bwd(o, **ca_bwd)
         o.w_layer, o.scale = w_layer, float(scale)
         o.flags = (L.RELU if relu else 0) | (L.RESIDUAL if res is not None else 0) | (L.MASK if mask is not None else 0) | \
                   (L.COLSUM if colsum is not None else 0)
@@ -522,6 +527,8 @@ class Chain:
             o.e = res
         if mask is not None:
             o.e = mask
+        if ca_bwd is not None:
+            o.flags |= L.CHAIN_CA_BWD_FUSED
         o.bias = self._ptr(bias)
         o.colsum = self._ptr(colsum)
         o.colsum_groups = colsum_groups
@@ -537,14 +544,22 @@ class Chain:
         o.ca_s, o.ca_y = self._ptr(s_out), self._ptr(y_out)
         return o
 
-    def ca_bwd(self, t, g, dt, w1, b1, w2, b2, s, y, dw1, db1, dw2, db2, scratch, colsum_dt=None):
-        o = self._op(L.CHAIN_CA_BWD, t, dt)
-        o.e = g
+    def _fill_ca_params(self, o, w1, b1, w2, b2, s, y, dw1, db1, dw2, db2, scratch):
         o.ca_cr = w1.shape[0]
         o.ca_w1, o.ca_b1, o.ca_w2, o.ca_b2 = self._ptr(w1), self._ptr(b1), self._ptr(w2), self._ptr(b2)
         o.ca_s, o.ca_y = self._ptr(s), self._ptr(y)
         o.ca_dw1, o.ca_db1, o.ca_dw2, o.ca_db2 = self._ptr(dw1), self._ptr(db1), self._ptr(dw2), self._ptr(db2)
         o.ca_scratch = self._ptr(scratch)
+
+    def _fill_ca_bwd(self, o, t, dt, w1, b1, w2, b2, s, y, dw1, db1, dw2, db2, scratch, colsum_dt=None):
+        self._fill_ca_params(o, w1, b1, w2, b2, s, y, dw1, db1, dw2, db2, scratch)
+        o.e2, o.y2 = t, dt
+        o.colsum2 = self._ptr(colsum_dt)
+
+    def ca_bwd(self, t, g, dt, w1, b1, w2, b2, s, y, dw1, db1, dw2, db2, scratch, colsum_dt=None):
+        o = self._op(L.CHAIN_CA_BWD, t, dt)
+        o.e = g
+        self._fill_ca_params(o, w1, b1, w2, b2, s, y, dw1, db1, dw2, db2, scratch)
         o.colsum = self._ptr(colsum_dt)
         return o
 

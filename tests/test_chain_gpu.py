@@ -158,6 +158,52 @@ def test_chain_ca_forward_and_backward(shape):
         assert _rel(a, b) < 1e-3
 
 
+@pytest.mark.parametrize("shape", [(16, 48, 48), (3, 20, 12)])
+def test_chain_conv_with_fused_ca_backward(shape):
+    """dgrad-style conv (+ residual) whose output g is dL/dout of an RCAB, with that RCAB's CALayer
+    backward fused into the same op (SRB_CHAIN_CA_BWD_FUSED), versus srb_conv + srb_ca_bwd.  g must be
+    bit-identical; dt / gradients within bf16 rounding of the reference kernels (gate summation order)."""
+    from srb200 import lib as L, ops
+    n, h, w = shape
+    bf = torch.bfloat16
+    cr = 4
+    x = _rand((n, h, w, 64), 0.02, seed=31).to(bf)
+    res = _rand((n, h, w, 64), 0.02, seed=32).to(bf)
+    t = _rand((n, h, w, 64), seed=33).to(bf)
+    wt = _rand((64, 64, 3, 3), 0.05, seed=34).contiguous()
+    cw1, cb1 = _rand((cr, 64), 0.2, seed=35), _rand((cr,), 0.1, seed=36)
+    cw2, cb2 = _rand((64, cr), 0.2, seed=37), _rand((64,), 0.1, seed=38)
+    s = _rand((n, 64), 0.3, seed=39)
+    yg = torch.sigmoid(_rand((n, 64), seed=40))
+    pk = ops.PackedWeights()
+    g = torch.empty_like(x)
+    ops.conv(x, 0, 64, pk, wt, None, g, 0, 64, 3, res=(res, 0))
+    dt = torch.empty_like(x)
+    gr = [torch.zeros_like(p) for p in (cw1, cb1, cw2, cb2)]
+    db2 = torch.zeros(64, device=DEV)
+    ops.ca_bwd(g, t, s, yg, cw1, cb1, cw2, cb2, dt, gr[0], gr[1], gr[2], gr[3], db2, torch.zeros(n, 64, device=DEV),
+               accumulate=True, scratch_is_zero=True)
+    bank = ops.FilterBank().get([(wt, pk)], L.PACK_FWD)
+    A = torch.zeros((2, n, h, w, 64), dtype=bf, device=DEV)
+    E = torch.stack([x, res, t]).contiguous()
+    gr2 = [torch.zeros_like(p) for p in (cw1, cb1, cw2, cb2)]
+    db2c = torch.zeros(64, device=DEV)
+    ch = ops.Chain(n, h, w, x.device)
+    ch.space(0, A)
+    ch.space(1, E)
+    ref = ops.Chain.ref
+    ch.conv(ref(1, 0), ref(0, 0), 0, None, res=ref(1, 1),
+            ca_bwd=dict(t=ref(1, 2), dt=ref(0, 1), w1=cw1, b1=cb1, w2=cw2, b2=cb2, s=s, y=yg, dw1=gr2[0], db1=gr2[1],
+                        dw2=gr2[2], db2=gr2[3], scratch=torch.zeros(n, 64, device=DEV), colsum_dt=db2c))
+    ch.run(bank)
+    torch.cuda.synchronize()
+    assert torch.equal(A[0], g)
+    assert _rel(A[1], dt) < 2e-3
+    assert _rel(db2c, db2) < 2e-3
+    for a, b in zip(gr2, gr):
+        assert _rel(a, b) < 1e-3
+
+
 def test_chain_rejects_bad_programs():
     from srb200 import lib as L, ops
     n, h, w = 1, 16, 8
