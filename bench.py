@@ -37,6 +37,10 @@ for p in (ROOT, PKG):
 
 import torch  # noqa: E402
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one conv_chain_kernel launch (ncu --set full,
+# profiles/r01_ncu_conv_chain_v4.txt); None until that capture exists
+CHAIN_TRAFFIC_BYTES = 247.3e6
+
 METRIC = "RCAN x4 train patches/sec (16x 48x48 LR patches per GPU per step, fwd+L1+bwd+Adam)"
 
 
@@ -191,38 +195,54 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def time_dominant_kernel(dev, launches=400):
-    """tcgen05 conv 3x3 64->64 (+bias+ReLU) on [16,48,48,64] bf16, alone on the stream.  Inputs
-    rotate over 48 buffer pairs (48 x 2 x 4.7 MB > 126 MB L2), i.e. operands come from HBM."""
-    from srb200 import lib as L, ops
-    nbuf = 48
-    xs = [torch.randn(BATCH, LR, LR, 64, device=dev).to(torch.bfloat16) for _ in range(nbuf)]
-    ys = [torch.empty(BATCH, LR, LR, 64, device=dev, dtype=torch.bfloat16) for _ in range(nbuf)]
-    w = torch.randn(64, 64, 3, 3, device=dev) * 0.04
-    b = torch.zeros(64, device=dev)
-    packs = ops.PackedWeights()
-    for i in range(8):
-        ops.conv(xs[i], 0, 64, packs, w, b, ys[i], 0, 64, 3, relu=True, backend=L.BACKEND_UMMA)
-    torch.cuda.synchronize()
-    # the launches are captured into a CUDA graph so the host (Python + ctypes, ~10 us per call)
-    # is out of the timed region: what the events bracket is back-to-back kernel execution
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.stream(side):
-        with torch.cuda.graph(graph):
-            for i in range(launches):
-                ops.conv(xs[i % nbuf], 0, 64, packs, w, b, ys[i % nbuf], 0, 64, 3, relu=True, backend=L.BACKEND_UMMA)
-        graph.replay()
+def time_dominant_kernel(dev, reps=10):
+    """The kernel that carries the step: conv_chain_kernel, one persistent launch per RCAN ResidualGroup
+    and direction (20 RCAB + tail conv = 41 tcgen05 3x3 64->64 convs on [16,48,48,64] bf16, CALayer
+    forward / backward fused in).  Timed alone with CUDA events over graph replays; the activations of
+    a launch (3.1 GB of arena per direction across the 10 groups of a step; 289 MB per launch) exceed
+    the 126 MB L2, and `reps` distinct input/arena sets rotate.  Returns (us forward launch, us backward
+    launch, algorithmic FLOP per launch)."""
+    import models
+    from srb200 import ops
+    torch.manual_seed(0)
+    grp = models.rcan.ResidualGroup(64, 3, 16, 1, 20).to(dev)
+    bf = torch.bfloat16
+    xs = [torch.randn(BATCH, LR, LR, 64, device=dev).to(bf).requires_grad_(True) for _ in range(reps)]
+    gs = [(torch.randn(BATCH, LR, LR, 64, device=dev) * 0.01).to(bf) for _ in range(reps)]
+
+    def timed(fn):
+        fn()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        graph.replay()
-        e1.record()
-        torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) * 1e3 / launches
-    flop = 2.0 * BATCH * LR * LR * 64 * 64 * 9
-    return us, flop
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph):
+                fn()
+            graph.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / reps
+
+    def fwd():
+        with torch.no_grad():
+            for x in xs:
+                grp(x)
+
+    def fwd_bwd():
+        # weight-gradient launches are queued and dropped: only the chain launches (+ one 5 us skip add) run
+        with ops.deferred_wgrads() as q:
+            for x, g in zip(xs, gs):
+                grp(x).backward(g)
+            q.items.clear()
+    us_f = timed(fwd)
+    us_fb = timed(fwd_bwd)
+    flop = 41 * 2.0 * BATCH * LR * LR * 64 * 64 * 9
+    return us_f, us_fb - us_f, flop
 
 
 def run_ours(args):
@@ -309,13 +329,23 @@ def run_ours(args):
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
 
-    if rank != 0:
+    def finish():
+        """Leave together: every rank meets at one last barrier (rank 0 arrives after its rank-0-only
+        measurements), then exits without running NCCL's teardown — a rank that tears its communicator
+        down while a peer is still busy can block both (seen as a torchrun that never returns)."""
         if world > 1:
-            dist.destroy_process_group()
+            sys.stdout.flush()
+            dist.barrier()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     peaks = measured_peaks()
-    k_us, k_flop = time_dominant_kernel(dev)
+    ms_step = ms_total / args.steps
+    k_us_f, k_us_b, k_flop = time_dominant_kernel(dev)
+    k_us = 0.5 * (k_us_f + k_us_b)             # a step launches it 10x forward + 10x backward
     k_tflops = k_flop / (k_us * 1e-6) / 1e12
     ms_step = ms_total / args.steps
     value = BATCH * world * args.steps / (ms_total / 1e3)
@@ -327,7 +357,8 @@ def run_ours(args):
         "data": "synthetic",
         "config": {
             "workload": f"{cls} x4 training step (BASELINE.json configs[2]): {kw}, batch {BATCH} x 3x{LR}x{LR} LR per GPU, "
-                        f"L1 loss, Adam lr=1e-3, bf16 activations / fp32 accumulate+master weights",
+                        f"L1 loss, Adam lr=1e-3, bf16 activations / fp32 accumulate+master weights; "
+                        f"64-channel trunks run as layer-chain launches (srb_conv_chain){'' if os.environ.get('SRB200_NO_CHAIN', '0') in ('', '0') else ' [disabled]'}",
             "parallelism": f"dp{world}", "cuda_graph": step.graph is not None,
             "l2": f"no explicit flush: one step streams {peak_mem / 2**30:.2f} GiB of saved activations and gradients "
                   f"(>> 126 MB L2); 4 distinct input batches rotate",
@@ -338,24 +369,29 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": k_tflops, "peak": peaks["burst"], "unit": "TFLOP/s",
-                     "frac": k_tflops / peaks["burst"], "traffic": None,
-                     "kernel": "conv_umma_kernel<64> 3x3 64->64 +bias+ReLU on [16,48,48,64] bf16, timed alone, "
-                               "operands from HBM (48 rotating buffers)",
-                     "us_per_launch": k_us, "flop_per_launch": k_flop, "peak_source": peaks["source"]},
+                     "frac": k_tflops / peaks["burst"], "traffic": CHAIN_TRAFFIC_BYTES,
+                     "kernel": "conv_chain_kernel: one RCAN ResidualGroup (20 RCAB + conv = 41 tcgen05 3x3 64->64 convs, "
+                               "CALayer fused) per launch on [16,48,48,64] bf16; average of the forward and the backward "
+                               "launch, timed alone over graph replays of 10 rotating arena sets (2.9 GB > L2)",
+                     "us_per_launch": k_us, "us_forward_launch": k_us_f, "us_backward_launch": k_us_b,
+                     "flop_per_launch": k_flop, "launches_per_step": 20,
+                     "share_of_step": 10.0 * (k_us_f + k_us_b) / (ms_step * 1e3),
+                     "traffic_note": "dram__bytes_read+write per launch from profiles/r01_ncu_conv_chain_v4.txt",
+                     "peak_source": peaks["source"]},
         "roofline_step": {"bound": "tensor", "achieved": step_tflops, "peak": peaks["sustained"], "unit": "TFLOP/s",
                           "frac": step_tflops / peaks["sustained"],
                           "note": f"whole step: {gflop_patch} algorithmic GFLOP/patch x {BATCH} / ms_per_step, vs sustained bf16 peak"},
     }
     if world == 1 and not args.no_cpu_baseline:
         try:
-            pps, ms = time_cpu_port(args.model, 2, 2, 1)
+            pps, ms = time_cpu_port(args.model, BATCH, 5, 1)
             line["cpu_baseline"] = {"value": pps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": "2 steps x 2 patches (48x48 LR) after 1 warm-up, fwd+L1+bwd+Adam, torch CPU fp32"}
+                                    "sample": f"5 steps x {BATCH} patches (48x48 LR) after 1 warm-up (~{6 * ms / 1e3:.0f} s of CPU work), "
+                                              "fwd+L1+bwd+Adam, torch CPU fp32, all host threads"}
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def main():

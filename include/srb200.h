@@ -179,7 +179,7 @@ typedef struct srb_chain_op {
   float    scale;
   int32_t  colsum_groups;   /* 1 -> colsum[64]; N -> colsum[N][64] (always N with SRB_CHAIN_CA) */
   int32_t  ca_cr;           /* hidden width of the CALayer (channel / reduction) */
-  int32_t  reserved1;
+  float    colsum_scale;    /* factor on the COLSUM contribution (res_scale on a bias gradient); 0 means 1 */
   const float* bias;        /* [64] or NULL */
   float*   colsum;
   float*   colsum2;         /* SRB_CHAIN_CA_BWD_FUSED: [64] column sums of dt, or NULL */

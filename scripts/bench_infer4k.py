@@ -65,7 +65,9 @@ def main():
                           "n_gpus": world, "ms_per_frame": ms, "tflops": gflop / ms, "local_parts": args.local_parts,
                           "dtype": "bf16", "data": "synthetic"}))
     if world > 1:
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        dist.barrier()
+        os._exit(0)          # leave together, without NCCL teardown ordering hazards
 
 
 if __name__ == "__main__":

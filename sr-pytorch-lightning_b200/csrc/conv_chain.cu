@@ -604,7 +604,8 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
           ptx::named_bar_sync(bar_id, 128);
           if ((flags & SRB_COLSUM) && row < 64) {
             const float tot = (colsum_s[c][0][row] + colsum_s[c][1][row]) + (colsum_s[c][2][row] + colsum_s[c][3][row]);
-            atomicAdd(o.colsum + (int64_t)(o.colsum_groups > 1 ? n : 0) * 64 + row, tot);
+            atomicAdd(o.colsum + (int64_t)(o.colsum_groups > 1 ? n : 0) * 64 + row,
+                      o.colsum_scale != 0.f ? tot * o.colsum_scale : tot);
           }
           if (ca) ptx::named_bar_sync(bar_id, 128);   // pooled-sum contributions precede the cumulative release below
           if (!ca) {

@@ -29,15 +29,49 @@ class EDSR(SRModel):
         self.body = nn.Sequential(*body)
         self.tail = nn.Sequential(UpscaleBlock(self._scale_factor, n_feats), DefaultConv2d(n_feats, self._channels, k))
 
+    def filter_bank(self, mode):
+        """Contiguous packed 3x3 filters of the body in chain order: (conv1, conv2) per ResBlock, tail."""
+        from srb200 import ops
+        if not hasattr(self, "_bank"):
+            self._bank = ops.FilterBank()
+        blocks = list(self.body)
+        convs = []
+        for blk in blocks[:-1]:
+            convs.append((blk.body[0].weight, blk.body[0].packs))
+            convs.append((blk.body[2].weight, blk.body[2].packs))
+        convs.append((blocks[-1].weight, blocks[-1].packs))
+        return self._bank.get(convs, mode)
+
+    def _chain_ok(self, x) -> bool:
+        import torch
+        blocks = list(self.body)
+        if not (F200.chain_enabled() and x.is_cuda and x.dtype == torch.bfloat16 and x.shape[3] == 64 and len(blocks) >= 2):
+            return False
+        for blk in blocks[:-1]:
+            if float(blk.res_scale) != float(blocks[0].res_scale):
+                return False
+            for conv in (blk.body[0], blk.body[2]):
+                if tuple(conv.weight.shape) != (64, 64, 3, 3) or conv.bias is None:
+                    return False
+        return tuple(blocks[-1].weight.shape) == (64, 64, 3, 3) and blocks[-1].bias is not None
+
     def forward(self, x):
         rgb = self._channels == 3
         x = F200.ToNHWC.apply(x, self.sub_mean.channel_add() if rgb else None, self.act_dtype)
         x = self.head[0](x)
         res = x
         blocks = list(self.body)
-        for blk in blocks[:-1]:
-            res = blk(res)
-        res = blocks[-1](res, residual=x)           # body tail conv + global skip (edsr.py:46-47)
+        if self._chain_ok(x):
+            # 64-channel trunk: the whole body (blocks + conv + global skip) is one persistent launch
+            params = []
+            for blk in blocks[:-1]:
+                params += [blk.body[0].weight, blk.body[0].bias, blk.body[2].weight, blk.body[2].bias]
+            params += [blocks[-1].weight, blocks[-1].bias]
+            res = F200.ResTrunkFn.apply(x, self, float(blocks[0].res_scale), *params)
+        else:
+            for blk in blocks[:-1]:
+                res = blk(res)
+            res = blocks[-1](res, residual=x)       # body tail conv + global skip (edsr.py:46-47)
         y = self.tail[0](res)
         y = self.tail[1](y)
         return F200.ToNCHW.apply(y, self.add_mean.channel_add() if rgb else None, self._channels)

@@ -325,6 +325,89 @@ class RCANGroupFn(Function):
         return (dx, None, *grads)
 
 
+class ResTrunkFn(Function):
+    """EDSR body (edsr.py:27-30,46-47): n x ResBlock (common.py:74-109: conv-ReLU-conv, * res_scale,
+    += x) + conv + global skip, forward and backward each as ONE chain launch (64-channel bf16).
+
+    Forward space 0 ("A", saved): slot 2b = relu(conv1_b), 2b+1 = block output; slot 2n = trunk output.
+    Backward space 0 ("B"): slot 2b = d(relu(conv1_b)) (masked, scaled), 2b+1 = dL/d(block input);
+    slot 2n = dL/d(last block output).  params = per block (w1, b1, w2, b2), then (w_tail, b_tail)."""
+
+    @staticmethod
+    def forward(ctx, x, owner, scale: float, *params):
+        x = x.contiguous()
+        n, h, w, c = x.shape
+        assert c == 64 and x.dtype == torch.bfloat16
+        nb = (len(params) - 2) // 4
+        dev = x.device
+        A = torch.empty((2 * nb + 1, n, h, w, 64), dtype=x.dtype, device=dev)
+        bank = owner.filter_bank(L.PACK_FWD)
+        ch = ops.Chain(n, h, w, dev)
+        ch.space(0, A)
+        ch.space(2, x.view(1, n, h, w, 64))
+        ref = ops.Chain.ref
+        xin = ref(2, 0)
+        cur = xin
+        for b in range(nb):
+            w1, b1, w2, b2 = (t.detach() for t in params[4 * b:4 * b + 4])
+            ch.conv(cur, ref(0, 2 * b), 2 * b, b1, relu=True)
+            ch.conv(ref(0, 2 * b), ref(0, 2 * b + 1), 2 * b + 1, b2, scale=scale, res=cur)
+            cur = ref(0, 2 * b + 1)
+        ch.conv(cur, ref(0, 2 * nb), 2 * nb, params[-1].detach(), res=xin)
+        ch.run(bank)
+        ctx.save_for_backward(x, A, *params)
+        ctx.owner, ctx.nb, ctx.scale = owner, nb, scale
+        return A[2 * nb]
+
+    @staticmethod
+    def backward(ctx, g):
+        x, A, *params = ctx.saved_tensors
+        nb, owner, scale = ctx.nb, ctx.owner, ctx.scale
+        g = g.contiguous()
+        _, n, h, w, _ = A.shape
+        dev = g.device
+        B = torch.empty((2 * nb + 1, n, h, w, 64), dtype=A.dtype, device=dev)
+        bank = owner.filter_bank(L.PACK_DGRAD)
+        ch = ops.Chain(n, h, w, dev)
+        ch.space(0, B)
+        ch.space(1, A)
+        ch.space(2, g.view(1, n, h, w, 64))
+        ref = ops.Chain.ref
+        grads = [None] * len(params)
+        wq = []   # (x, gy, weight index, bias index or None, alpha)
+
+        def b2_target(b):
+            """bias gradient of block b's second conv = res_scale * column sums of dL/d(block output)."""
+            buf, grads[4 * b + 3] = _zeroed_grad_target(params[4 * b + 3])
+            return buf
+
+        ch.conv(ref(2, 0), ref(0, 2 * nb), 2 * nb, colsum=b2_target(nb - 1), colsum_scale=scale)
+        wq.append((A[2 * nb - 1], g, len(params) - 2, len(params) - 1, 1.0))
+        gslot = 2 * nb
+        for b in range(nb - 1, -1, -1):
+            db1, grads[4 * b + 1] = _zeroed_grad_target(params[4 * b + 1])
+            ch.conv(ref(0, gslot), ref(0, 2 * b), 2 * b + 1, scale=scale, mask=ref(1, 2 * b), colsum=db1)
+            if b > 0:
+                ch.conv(ref(0, 2 * b), ref(0, 2 * b + 1), 2 * b, res=ref(0, gslot), colsum=b2_target(b - 1), colsum_scale=scale)
+            else:
+                ch.conv(ref(0, 2 * b), ref(0, 2 * b + 1), 2 * b, res=ref(0, gslot))
+            wq.append((A[2 * b], B[gslot], 4 * b + 2, None, scale))
+            wq.append((A[2 * b - 1] if b > 0 else x, B[2 * b], 4 * b, None, 1.0))
+            gslot = 2 * b + 1
+        ch.run(bank)
+        for xt, gy, wi, bi, alpha in wq:
+            wbuf, acc, grads[wi] = _grad_target(params[wi])
+            bbuf = None
+            if bi is not None:
+                bbuf, _, grads[bi] = _grad_target(params[bi])
+            ops.conv_wgrad(xt, 0, 64, gy, 0, 64, 3, wbuf, bbuf, accumulate=acc, alpha=alpha)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(g)
+            ops.add_channels(B[1], 0, g, 0, dx, 0, 64)
+        return (dx, None, None, *grads)
+
+
 class RDBFn(Function):
     """RDN residual dense block (rdn.py:24-40).  The C dense layers read a channel prefix of ONE
     [N,H,W,G0+C*G] buffer and write their G new channels in place (no torch.cat, rdn.py:21);

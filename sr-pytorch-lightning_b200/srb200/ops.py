@@ -514,7 +514,7 @@ class Chain:
         return t.data_ptr()
 
     def conv(self, x, y, w_layer, bias=None, *, relu=False, scale=1.0, res=None, mask=None, colsum=None, colsum_groups=1,
-             ca_bwd=None):
+             colsum_scale=1.0, ca_bwd=None):
         """ca_bwd: dict(t=ref, dt=ref, w1, b1, w2, b2, s, y, dw1, db1, dw2, db2, scratch, colsum_dt) — fuse the
         CALayer backward of the block whose dL/dout this conv produces (SRB_CHAIN_CA_BWD_FUSED)."""
         o = self._op(L.CHAIN_CONV, x, y)
@@ -532,6 +532,7 @@ class Chain:
         o.bias = self._ptr(bias)
         o.colsum = self._ptr(colsum)
         o.colsum_groups = colsum_groups
+        o.colsum_scale = float(colsum_scale)
         return o
 
     def conv_ca(self, x, t, out, skip, w_layer, bias, pool, w1, b1, w2, b2, s_out, y_out):

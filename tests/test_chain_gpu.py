@@ -253,3 +253,36 @@ def test_rcan_chain_path_matches_layer_path(cfg, monkeypatch):
     num = sum(float(((res["chain"][2][k] - v) ** 2).sum()) for k, v in res["layers"][2].items())
     den = sum(float((v ** 2).sum()) for v in res["layers"][2].values())
     assert (num / den) ** 0.5 < 2e-2
+
+
+@pytest.mark.parametrize("cfg", [dict(n_resblocks=16, res_scale=1.0), dict(n_resblocks=3, res_scale=0.1),
+                                 dict(n_resblocks=34, res_scale=0.5)])
+def test_edsr_chain_path_matches_layer_path(cfg, monkeypatch):
+    """EDSR 64-channel body as one chain launch per direction vs the per-layer path.  Every op is a
+    plain conv with the same MMA order and epilogue arithmetic, so outputs agree bit for bit and
+    gradients to fp32 atomics order (weight gradients come from the same wgrad kernel on identical
+    operands; bias gradients are column sums accumulated in a different order)."""
+    import models
+    torch.manual_seed(0)
+    kw = dict(n_feats=64, scale_factor=4, **cfg)
+    m0 = models.EDSR(**kw)
+    sd = {k: v.clone() for k, v in m0.state_dict().items()}
+    x = torch.rand(4, 3, 24, 24)
+    hr = torch.rand(4, 3, 96, 96)
+    res = {}
+    for mode in ("chain", "layers"):
+        monkeypatch.setenv("SRB200_NO_CHAIN", "0" if mode == "chain" else "1")
+        m = models.EDSR(**kw)
+        m.load_state_dict(sd)
+        m.compute_dtype = "bf16"
+        m = m.to(DEV)
+        out = m.training_step({"lr": x.to(DEV), "hr": hr.to(DEV)}, 0)
+        out["loss"].backward()
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            sr = m.forward(x.to(DEV)).float().cpu()
+        res[mode] = (sr, out["loss"].item(), {k: p.grad.double().cpu() for k, p in m.named_parameters() if p.requires_grad})
+    assert torch.equal(res["chain"][0], res["layers"][0])
+    assert abs(res["chain"][1] - res["layers"][1]) < 1e-6 * abs(res["layers"][1])   # L1 sum: fp32 atomics order
+    for k, v in res["layers"][2].items():
+        assert _rel(res["chain"][2][k], v) < 1e-4, k

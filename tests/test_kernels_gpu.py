@@ -449,3 +449,33 @@ def test_conv_wgrad_batched_deferred():
     torch.cuda.synchronize()
     for (dw, db), (rw, rb) in zip(got, ref):
         assert _rel(dw, rw)[0] < 1e-5 and _rel(db, rb)[0] < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 3), (256, 64, 3), (64, 576, 1), (64, 40, 3), (3, 64, 3), (64, 3, 3)])
+def test_pack_table_matches_pack_weight(shape):
+    """srb_pack_table (one launch re-packing many weights, used once per optimizer step) must write
+    exactly the bytes srb_pack_weight writes, for every packing / mode / shuffle, including the
+    zero-padded partial 64-channel chunk."""
+    import ctypes as C
+    import numpy as np
+    from srb200 import lib as L, ops
+    cout, cin, k = shape
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(7)
+    w = torch.randn(cout, cin, k, k, generator=g).to(dev)
+    rows, keep = [], []
+    for packing in (L.PACK_SIMT, L.PACK_UMMA):
+        for mode in (L.PACK_FWD, L.PACK_DGRAD):
+            for shuffle in ((0, 2) if cout % 4 == 0 else (0,)):
+                want = ops.pack_weight(w, packing, mode, shuffle)
+                got = torch.zeros_like(want)       # UMMA padding of a partial chunk stays as first packed (zeros)
+                rows.append((w.data_ptr(), got.data_ptr(), cout, cin, k, packing, mode, shuffle))
+                keep.append((want, got, packing, mode, shuffle))
+    dt = np.dtype([("src", "<u8"), ("dst", "<u8"), ("Cout", "<i4"), ("Cin", "<i4"), ("ksize", "<i4"),
+                   ("packing", "<i4"), ("mode", "<i4"), ("shuffle", "<i4")])
+    table = torch.from_numpy(np.array(rows, dtype=dt).view(np.uint8).copy()).to(dev)
+    L.check(L.load().srb_pack_table(C.c_void_p(L.ctx(0)), C.c_void_p(table.data_ptr()), len(rows), w.numel(),
+                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)), "srb_pack_table")
+    torch.cuda.synchronize()
+    for want, got, packing, mode, shuffle in keep:
+        assert torch.equal(want, got), (packing, mode, shuffle)
