@@ -238,7 +238,7 @@ def time_dominant_kernel(dev, reps=10):
         with ops.deferred_wgrads() as q:
             for x, g in zip(xs, gs):
                 grp(x).backward(g)
-            q.items.clear()
+                q.items.clear()
     us_f = timed(fwd)
     us_fb = timed(fwd_bwd)
     flop = 41 * 2.0 * BATCH * LR * LR * 64 * 64 * 9

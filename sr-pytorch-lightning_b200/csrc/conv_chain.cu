@@ -151,6 +151,34 @@ __device__ __forceinline__ void mma_tile(uint32_t tmem_d, uint32_t a_lo, uint32_
   }
 }
 
+// Column sums of a staged tile ([128 pixels][64 ch] bf16, 16-byte chunks XOR-swizzled by pixel & 7) read
+// back from shared memory: warp q sums its 32 rows; lane = (chunk k = lane & 7, row phase lane >> 3), eight
+// conflict-free 16-byte loads per lane, two shuffle levels; lanes 0-7 then hold channels 8k..8k+7 and write
+// them to out[64].  Used AFTER the tile's TMA store has been issued, i.e. off the op's critical path
+// (a butterfly over the epilogue registers costs ~1 us before the store).
+__device__ __forceinline__ void tile_colsum_lds(uint32_t tile, int q, int lane, float* out) {
+  const int k = lane & 7, rp = lane >> 3;
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = q * 32 + rp + 4 * i;
+    const uint4 v = ptx::lds128(tile + (uint32_t)r * 128u + (uint32_t)((k ^ (r & 7)) << 4));
+    const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y), f2 = unpack_bf16x2(v.z), f3 = unpack_bf16x2(v.w);
+    a[0] += f0.x; a[1] += f0.y; a[2] += f1.x; a[3] += f1.y; a[4] += f2.x; a[5] += f2.y; a[6] += f3.x; a[7] += f3.y;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a[j] += __shfl_xor_sync(0xffffffffu, a[j], 8);
+    a[j] += __shfl_xor_sync(0xffffffffu, a[j], 16);
+  }
+  if (rp == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[k * 8 + j] = a[j];
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -348,7 +376,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
 
         // CALayer + skip backward on one tile (rcan.py:10-29,54): g_row / t_row = this thread's 128-byte rows
         // of dL/dout and of the saved pre-attention tensor; dt = g*gate + ds/HW is written to out_row.
-        auto ca_bwd_tile = [&](const uint32_t g_row, const uint32_t t_row, const uint32_t out_row, float* colsum_dt) {
+        auto ca_bwd_tile = [&](const uint32_t g_row, const uint32_t t_row, const uint32_t out_row) {
 #pragma unroll 1
           for (int c0 = 0; c0 < 64; c0 += 32) {
             float s[32];
@@ -479,23 +507,15 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
               }
               ptx::sts128(out_row + off, make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]));
             }
-            if (colsum_dt) {
-              float s[32];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float2 f = unpack_bf16x2(packed[i]);
-                s[2 * i] = f.x;
-                s[2 * i + 1] = f.y;
-              }
-              colsum_s[c][q][c0 + lane] = warp_colsum32(s, lane);
-            }
           }
-          if (colsum_dt) {
-            ptx::named_bar_sync(bar_id, 128);
-            if (row < 64) {
-              const float tot = (colsum_s[c][0][row] + colsum_s[c][1][row]) + (colsum_s[c][2][row] + colsum_s[c][3][row]);
-              atomicAdd(colsum_dt + row, tot);
-            }
+        };
+        // column sums of a tile already handed to a TMA store (read-only here), accumulated into dst[64]
+        auto late_colsum = [&](const uint32_t tile, float* dst, const float factor) {
+          tile_colsum_lds(tile, q, lane, colsum_s[c][q]);
+          ptx::named_bar_sync(bar_id, 128);
+          if (row < 64) {
+            const float tot = (colsum_s[c][0][row] + colsum_s[c][1][row]) + (colsum_s[c][2][row] + colsum_s[c][3][row]);
+            atomicAdd(dst + row, factor != 0.f ? tot * factor : tot);
           }
         };
 
@@ -573,9 +593,10 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
               for (int g = 0; g < 4; ++g)
                 ptx::sts128(orow + ((((uint32_t)(c0 >> 3) + g) ^ sw) << 4),
                             make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]));
-              if (fl & SRB_COLSUM) {
-                // sums of the STORED (bf16-rounded) values over this warp's 32 pixels; the four warps'
-                // partial sums meet in shared memory so that a tile issues 64 atomics, not 256
+              if ((fl & SRB_COLSUM) && (fl & SRB_CHAIN_CA)) {
+                // CALayer pool (needed before anything else can happen): sums of the STORED (bf16-rounded)
+                // values over this warp's 32 pixels; the four warps' partial sums meet in shared memory so
+                // that a tile issues 64 atomics, not 256.  Other column sums are taken after the store.
                 float s[32];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -602,12 +623,13 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
           ptx::tc_fence_before();
           ptx::fence_proxy_async_smem();
           ptx::named_bar_sync(bar_id, 128);
-          if ((flags & SRB_COLSUM) && row < 64) {
-            const float tot = (colsum_s[c][0][row] + colsum_s[c][1][row]) + (colsum_s[c][2][row] + colsum_s[c][3][row]);
-            atomicAdd(o.colsum + (int64_t)(o.colsum_groups > 1 ? n : 0) * 64 + row,
-                      o.colsum_scale != 0.f ? tot * o.colsum_scale : tot);
+          if (ca) {
+            if (row < 64) {
+              const float tot = (colsum_s[c][0][row] + colsum_s[c][1][row]) + (colsum_s[c][2][row] + colsum_s[c][3][row]);
+              atomicAdd(o.colsum + (int64_t)n * 64 + row, tot);
+            }
+            ptx::named_bar_sync(bar_id, 128);   // pooled-sum contributions precede the cumulative release below
           }
-          if (ca) ptx::named_bar_sync(bar_id, 128);   // pooled-sum contributions precede the cumulative release below
           if (!ca) {
             if (store_thread) {
               ptx::mbar_arrive(&acc_empty[c]);
@@ -616,18 +638,21 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
               ptx::bulk_commit_group();
               CH_TRACE(c, op, TR_STAGED);
             }
+            if (flags & SRB_COLSUM)
+              late_colsum(stg, o.colsum + (int64_t)(o.colsum_groups > 1 ? n : 0) * 64, o.colsum_scale);
             if (flags & SRB_CHAIN_CA_BWD_FUSED) {
               // y (just staged, bf16) is dL/dout of the previous RCAB: run its CALayer backward here
               // instead of as a dependent op.  The staging buffer is only READ (the store of y may
               // still be reading it too); dt overwrites the t tile and is stored from there.
               ptx::mbar_wait(&e2_full[c], e2_k & 1u);
-              ca_bwd_tile(orow, e2row, e2row, o.colsum2);
+              ca_bwd_tile(orow, e2row, e2row);
               ptx::fence_proxy_async_smem();
               ptx::named_bar_sync(bar_id, 128);
               if (store_thread) {
                 tma_store_5d(&maps.tile[ref_space(o.y2)], e2buf, 0, w0, h0, n, ref_slot(o.y2));
                 ptx::bulk_commit_group();
               }
+              if (o.colsum2) late_colsum(e2buf, o.colsum2, 0.f);
               ++e2_k;
             }
           } else {
@@ -720,7 +745,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
           // ---- CALayer + skip backward (tile op, no MMA): x = t tile (window buffer), e = g tile ----
           ptx::mbar_wait(&a_full[c], a_k & 1u);
           ptx::mbar_wait(&e_full[c], e_k & 1u);
-          ca_bwd_tile(erow, trow, orow, o.colsum);
+          ca_bwd_tile(erow, trow, orow);
           ptx::fence_proxy_async_smem();
           ptx::named_bar_sync(bar_id, 128);
           if (store_thread) {
@@ -729,6 +754,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
             tma_store_5d(&maps.tile[ref_space(o.y)], stg, 0, w0, h0, n, ref_slot(o.y));
             ptx::bulk_commit_group();
           }
+          if (o.colsum) late_colsum(stg, o.colsum, 0.f);
           ++e_k;
         }
         ++a_k;
