@@ -481,6 +481,9 @@ int srb_conv_umma_bn(const srb_conv_desc* d) {
 }
 
 int srb_conv_c64_ok(const srb_conv_desc* d);
+int srb_conv_wide_ok(const srb_conv_desc* d);
+int srb_conv_wide(srb_ctx*, const srb_conv_desc*, const void*, const void*, const float*, const void*, const void*, void*,
+                  cudaStream_t);
 int srb_conv_c64(srb_ctx*, const srb_conv_desc*, const void*, const void*, const float*, const void*, const void*, void*,
                  void*, float*, cudaStream_t);
 
@@ -488,6 +491,8 @@ int srb_conv_umma(srb_ctx* ctx, const srb_conv_desc* d, const void* x, const voi
                   const void* res, const void* mask, void* y, void* y2, float* colsum, cudaStream_t st) {
   // hot shape (3x3, <=64 -> 64 channels): persistent resident-filter kernel (conv_c64.cu)
   if (srb_conv_c64_ok(d) && !getenv("SRB200_NO_C64")) return srb_conv_c64(ctx, d, x, w, bias, res, mask, y, y2, colsum, st);
+  // wide layers (Cin % 64 == 0, Cout % 128 == 0): persistent kernel, two pixel tiles per filter stage (conv_wide.cu)
+  if (srb_conv_wide_ok(d) && !getenv("SRB200_NO_WIDE")) return srb_conv_wide(ctx, d, x, w, bias, res, mask, y, st);
   const int BN = srb_conv_umma_bn(d);
   SRB_REQUIRE(BN != 0, "srb_conv(umma): conv not eligible for the tcgen05 path (bf16, k in {1,3}, channel "
               "strides/offsets %% 8 == 0, Cout %% 16 == 0 or < 16, W >= 8): Cin=%d Cout=%d k=%d dtype=%d", d->Cin, d->Cout, d->ksize, d->dtype);

@@ -141,6 +141,12 @@ UMMA_CASES = [
     dict(n=16, h=48, w=48, cin=64, cout=64, k=3, relu=True),         # 288 tiles on 148 SMs: 2 tiles per CTA
     dict(n=16, h=48, w=48, cin=64, cout=64, k=3, colsum=2, mask=True),
     dict(n=7, h=50, w=45, cin=64, cout=64, k=3, scale=0.5, residual=True),   # ragged, 3+ tiles per CTA
+    # wide-layer kernel (conv_wide.cu): two pixel tiles per filter stage, persistent, double-buffered TMEM
+    dict(n=1, h=40, w=72, cin=256, cout=256, k=3, scale=0.1, residual=True),       # EDSR-large ResBlock conv2, >148 items
+    dict(n=2, h=33, w=29, cin=256, cout=256, k=3, relu=True),                        # ragged pairs (W not a multiple of 16)
+    dict(n=1, h=16, w=32, cin=256, cout=1024, k=3, shuffle=2),                       # EDSR-large up-sampling conv
+    dict(n=1, h=17, w=16, cin=64, cout=128, k=3, mask=True),                         # one K chunk, masked (dgrad form)
+    dict(n=3, h=48, w=48, cin=128, cout=128, k=3, x_cs=576, x_co=64, y_cs=576, y_co=192, relu=True),  # channel slices
 ]
 
 
