@@ -24,12 +24,16 @@ constexpr int kThreads = 192;                        // TMA producer, MMA issuer
 constexpr int kTW = 8, kTH = 16;                     // one pixel tile = UMMA M = 128
 constexpr int kPairW = 2 * kTW;                      // two tiles side by side
 constexpr int kRows = kTH + 2;
-constexpr int BN = 128;
 constexpr uint32_t kABytes = kRows * kPairW * 128;   // 36864: one kw-shifted window, 64 channels
-constexpr uint32_t kBBytes = 3u * BN * 128u;         // 49152: three kh slices
-constexpr uint32_t kStageBytes = kABytes + kBBytes;  // 86016
-constexpr int kStages = 2;
-constexpr uint32_t kTmemCols = 512;                  // [2 buffers][2 tiles][128 columns]
+constexpr int kMaxStages = 3;
+// BN = 128: Cout a multiple of 128 (EDSR-large); BN = 64: the other multiples of 64 (RDN dense layers
+// 128..576 -> 64, the 64 -> 256 up-sampling convs whose PixelShuffle groups are 64 wide, their dgrads)
+template <int BN> struct WideCfg {
+  static constexpr uint32_t kBBytes = 3u * BN * 128u;            // three kh slices: 49152 / 24576
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;     // 86016 / 61440
+  static constexpr int kStages = BN == 128 ? 2 : 3;
+  static constexpr uint32_t kTmemCols = 4u * BN;                 // [2 buffers][2 tiles][BN columns]
+};
 
 struct WideParams {
   srb_conv_desc d;
@@ -40,6 +44,7 @@ struct WideParams {
   int pairs_w, tiles_h, n_tiles_n, total_items, nchunks;
 };
 
+template <int BN>
 __device__ __forceinline__ void item_coords(const WideParams& p, int item, int& n, int& h0, int& w0, int& n0) {
   const int nt = item % p.n_tiles_n;
   int pp = item / p.n_tiles_n;
@@ -52,7 +57,8 @@ __device__ __forceinline__ void item_coords(const WideParams& p, int item, int& 
   n0 = nt * BN;
 }
 
-// one 128-pixel x 128-cout accumulator -> global memory
+// one 128-pixel x BN-cout accumulator -> global memory
+template <int BN>
 __device__ __forceinline__ void wide_epilogue(const WideParams& p, uint32_t tmem_acc, int q, int lane, int n, int h0, int w0,
                                               int n0) {
   const srb_conv_desc& d = p.d;
@@ -130,10 +136,14 @@ __device__ __forceinline__ void wide_epilogue(const WideParams& p, uint32_t tmem
   }
 }
 
+template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WideParams p) {
+  constexpr uint32_t kBBytes = WideCfg<BN>::kBBytes, kStageBytes = WideCfg<BN>::kStageBytes, kTmemCols = WideCfg<BN>::kTmemCols;
+  constexpr int kStages = WideCfg<BN>::kStages;
+  (void)kBBytes;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[kStages], empty_bar[kStages];
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
   __shared__ uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
 
@@ -172,7 +182,7 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t it = 0;
       for (int i = 0; i < my_items; ++i) {
         int n, h0, w0, n0;
-        item_coords(p, (int)blockIdx.x + i * (int)gridDim.x, n, h0, w0, n0);
+        item_coords<BN>(p, (int)blockIdx.x + i * (int)gridDim.x, n, h0, w0, n0);
         for (int chunk = 0; chunk < p.nchunks; ++chunk) {
           for (int kw = 0; kw < 3; ++kw, ++it) {
             const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
@@ -196,7 +206,7 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t buf = (uint32_t)i & 1u;
         ptx::mbar_wait(&acc_empty[buf], (((uint32_t)i >> 1) & 1u) ^ 1u);
         ptx::tc_fence_after();
-        const uint32_t acc0 = tmem_base + buf * 256u;
+        const uint32_t acc0 = tmem_base + buf * (2u * BN);
         for (int ci = 0; ci < iters; ++ci, ++it) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
           ptx::mbar_wait(&full_bar[s], ph);
@@ -209,7 +219,7 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int t = 0; t < 2; ++t) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                ptx::umma_bf16_lohi(acc0 + (uint32_t)t * 128u, a_lo + (uint32_t)(kh * kPairW * 8 + t * 64 + k * 2), hi_a,
+                ptx::umma_bf16_lohi(acc0 + (uint32_t)t * (uint32_t)BN, a_lo + (uint32_t)(kh * kPairW * 8 + t * 64 + k * 2), hi_a,
                                     b_lo + (uint32_t)(kh * BN * 8 + k * 2), hi_b, idesc, (ci != 0 || kh != 0 || k != 0) ? 1u : 0u);
             }
           }
@@ -223,12 +233,12 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;
     for (int i = 0; i < my_items; ++i) {
       int n, h0, w0, n0;
-      item_coords(p, (int)blockIdx.x + i * (int)gridDim.x, n, h0, w0, n0);
+      item_coords<BN>(p, (int)blockIdx.x + i * (int)gridDim.x, n, h0, w0, n0);
       const uint32_t buf = (uint32_t)i & 1u;
       ptx::mbar_wait(&acc_full[buf], ((uint32_t)i >> 1) & 1u);
       ptx::tc_fence_after();
-      wide_epilogue(p, tmem_base + buf * 256u, q, lane, n, h0, w0, n0);
-      wide_epilogue(p, tmem_base + buf * 256u + 128u, q, lane, n, h0, w0 + kTW, n0);
+      wide_epilogue<BN>(p, tmem_base + buf * (2u * BN), q, lane, n, h0, w0, n0);
+      wide_epilogue<BN>(p, tmem_base + buf * (2u * BN) + (uint32_t)BN, q, lane, n, h0, w0 + kTW, n0);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&acc_empty[buf]);
     }
@@ -246,25 +256,41 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+template <int BN>
+int launch_wide(srb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const WideParams& p, cudaStream_t st) {
+  const size_t smem = (size_t)WideCfg<BN>::kStages * WideCfg<BN>::kStageBytes + 1024;
+  SRB_REQUIRE((int)smem <= ctx->smem_optin, "srb_conv(wide): needs %zu bytes of shared memory", smem);
+  static bool attr = false;
+  if (!attr) {
+    SRB_CHECK_CUDA(cudaFuncSetAttribute(conv_wide_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  const unsigned grid = (unsigned)(p.total_items < ctx->num_sms ? p.total_items : ctx->num_sms);
+  conv_wide_kernel<BN><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+  SRB_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace
 
-// 1 if the conv is a shape/flag combination this kernel handles (the caller falls back otherwise)
+// N-tile width this kernel would use for the conv (128 or 64), 0 if it does not handle it (the caller falls back)
 int srb_conv_wide_ok(const srb_conv_desc* d) {
   if (d->dtype != SRB_BF16 || d->ksize != 3) return 0;
   if (d->Cin < 64 || d->Cin % 64) return 0;
   const int rr = d->shuffle > 1 ? d->shuffle * d->shuffle : 1;
-  if (d->Cout % rr || (d->Cout / rr) % BN) return 0;
+  if (d->Cout % rr || (d->Cout / rr) % 64) return 0;
   if (d->flags & ~(SRB_RELU | SRB_RESIDUAL | SRB_MASK)) return 0;
   if (d->x_cs % 8 || d->x_co % 8 || d->y_cs % 8 || d->y_co % 8) return 0;
   if ((d->flags & SRB_RESIDUAL) && (d->r_cs % 8 || d->r_co % 8)) return 0;
   if ((d->flags & SRB_MASK) && (d->m_cs % 8 || d->m_co % 8)) return 0;
   if (d->W < kPairW || d->H < 1) return 0;
-  return 1;
+  return (d->Cout / rr) % 128 == 0 ? 128 : 64;
 }
 
 int srb_conv_wide(srb_ctx* ctx, const srb_conv_desc* d, const void* x, const void* w, const float* bias, const void* res,
                   const void* mask, void* y, cudaStream_t st) {
-  SRB_REQUIRE(srb_conv_wide_ok(d), "srb_conv(wide): conv not eligible");
+  const int bn = srb_conv_wide_ok(d);
+  SRB_REQUIRE(bn != 0, "srb_conv(wide): conv not eligible");
   SRB_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)res & 15) == 0 &&
                   ((uintptr_t)mask & 15) == 0,
               "srb_conv(wide): tensors must be 16-byte aligned");
@@ -276,7 +302,7 @@ int srb_conv_wide(srb_ctx* ctx, const srb_conv_desc* d, const void* x, const voi
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
   p.pairs_w = srb_cdiv(d->W, kPairW);
   p.tiles_h = srb_cdiv(d->H, kTH);
-  p.n_tiles_n = d->Cout / BN;
+  p.n_tiles_n = d->Cout / bn;
   p.nchunks = d->Cin / 64;
   const int64_t items = (int64_t)d->N * p.tiles_h * p.pairs_w * p.n_tiles_n;
   SRB_REQUIRE(items < (1ll << 31), "srb_conv(wide): too many work items");
@@ -298,22 +324,12 @@ int srb_conv_wide(srb_ctx* ctx, const srb_conv_desc* d, const void* x, const voi
     // packed weights [Cin/64][kw][kh][Cout][64]: 3-D view (cin, cout, chunk*9 + kw*3 + kh)
     cuuint64_t dims[3] = {64, (cuuint64_t)d->Cout, (cuuint64_t)p.nchunks * 9};
     cuuint64_t strides[2] = {128, (cuuint64_t)d->Cout * 128};
-    cuuint32_t box[3] = {64, (cuuint32_t)BN, 3};
+    cuuint32_t box[3] = {64, (cuuint32_t)bn, 3};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SRB_REQUIRE(r == CUDA_SUCCESS, "srb_conv(wide): cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r);
   }
-  const size_t smem = (size_t)kStages * kStageBytes + 1024;
-  SRB_REQUIRE((int)smem <= ctx->smem_optin, "srb_conv(wide): needs %zu bytes of shared memory", smem);
-  static bool attr = false;
-  if (!attr) {
-    SRB_CHECK_CUDA(cudaFuncSetAttribute(conv_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
-  const unsigned grid = (unsigned)(items < ctx->num_sms ? items : ctx->num_sms);
-  conv_wide_kernel<<<grid, kThreads, smem, st>>>(tmA, tmB, p);
-  SRB_LAUNCH_CHECK();
-  return 0;
+  return bn == 128 ? launch_wide<128>(ctx, tmA, tmB, p, st) : launch_wide<64>(ctx, tmA, tmB, p, st);
 }
