@@ -204,14 +204,29 @@ def time_dominant_kernel(dev, reps=10):
     launch, algorithmic FLOP per launch)."""
     import models
     from srb200 import ops
+    from srb200.trainer import FlatParams
     torch.manual_seed(0)
     grp = models.rcan.ResidualGroup(64, 3, 16, 1, 20).to(dev)
+    # gradients land in a flat buffer that is "live" (accumulating), as inside a training step: without it
+    # every small gradient tensor would get its own fill launch (~120 per group) and those, not the chain
+    # launch, would be timed (r01 v4 lines reported 826 us for the 336 us backward launch for this reason)
+    flat = FlatParams(grp)
+    flat.begin_step(zero=True)
+    arena = ops.ZeroArena(dev)
     bf = torch.bfloat16
     xs = [torch.randn(BATCH, LR, LR, 64, device=dev).to(bf).requires_grad_(True) for _ in range(reps)]
     gs = [(torch.randn(BATCH, LR, LR, 64, device=dev) * 0.01).to(bf) for _ in range(reps)]
 
-    def timed(fn):
+    def timed(fn0):
+        def fn():
+            ops.set_arena(arena)
+            try:
+                arena.reset()                     # one memset per graph replay (pooled sums / CA scratch)
+                fn0()
+            finally:
+                ops.set_arena(None)
         fn()
+        fn()                                      # second pass: the arena is sized now
         torch.cuda.synchronize()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -241,6 +256,7 @@ def time_dominant_kernel(dev, reps=10):
                 q.items.clear()
     us_f = timed(fwd)
     us_fb = timed(fwd_bwd)
+    flat.detach()
     flop = 41 * 2.0 * BATCH * LR * LR * 64 * 64 * 9
     return us_f, us_fb - us_f, flop
 

@@ -1,4 +1,5 @@
 // Dispatch of the convolution entry points (include/srb200.h) to the tcgen05 or CUDA-core kernels.
+#include <stdlib.h>
 #include <vector>
 
 #include "common.cuh"
@@ -14,6 +15,10 @@ int srb_wgrad_umma_ok(const srb_wgrad_desc*);
 int srb_wgrad_umma_batched(srb_ctx*, const srb_wgrad_desc*, const void* const*, const void* const*, float* const*, int,
                            cudaStream_t);
 int srb_colsum_launch(srb_ctx*, const void*, int, int, int, int64_t, int, float*, int, float, int, cudaStream_t);
+int srb_colsum_batched_ok(const void* x, int cs, int co, int C, int dtype);
+int srb_colsum_batched_launch(srb_ctx*, int n, const void* const* xs, const int* cs, const int* co, const int* C,
+                              const int64_t* npix, float* const* outs, const int* accumulate, const float* alpha,
+                              const int* shuffle, cudaStream_t st);
 
 static int check_conv_desc(const srb_conv_desc* d, const void* x, const void* w, const void* res, const void* mask,
                            void* y, void* y2, float* colsum) {
@@ -83,6 +88,17 @@ extern "C" int srb_conv_wgrad_batched(srb_ctx* ctx, const srb_wgrad_item* items,
   std::vector<srb_wgrad_desc> descs;
   std::vector<const void*> xs, gys;
   std::vector<float*> dws;
+  // bias gradients of the batch share one launch (misc.cu colsum_batched_kernel); SRB200_NO_BATCHED_COLSUM=1
+  // keeps one launch per bias (A/B measurements)
+  static const bool batch_colsums = [] {
+    const char* e = getenv("SRB200_NO_BATCHED_COLSUM");
+    return !(e && e[0] && e[0] != '0');
+  }();
+  std::vector<const void*> cx;
+  std::vector<int> ccs, cco, cC, cacc, cshuf;
+  std::vector<int64_t> cnp;
+  std::vector<float*> cout_;
+  std::vector<float> calpha;
   for (int i = 0; i < n; ++i) {
     const srb_wgrad_item& it = items[i];
     SRB_REQUIRE(it.x && it.gy && it.dw, "srb_conv_wgrad_batched: item %d has a null pointer", i);
@@ -93,14 +109,32 @@ extern "C" int srb_conv_wgrad_batched(srb_ctx* ctx, const srb_wgrad_item* items,
       gys.push_back(it.gy);
       dws.push_back(it.dw);
       if (it.dbias) {
-        int rc = srb_colsum_launch(ctx, it.gy, it.d.g_cs, it.d.g_co, it.d.Cout, (int64_t)it.d.N * it.d.H * it.d.W,
-                                   it.d.dtype, it.dbias, it.d.accumulate, it.d.alpha, it.d.shuffle, st);
-        if (rc) return rc;
+        const int64_t npix = (int64_t)it.d.N * it.d.H * it.d.W;
+        if (batch_colsums && srb_colsum_batched_ok(it.gy, it.d.g_cs, it.d.g_co, it.d.Cout, it.d.dtype)) {
+          cx.push_back(it.gy);
+          ccs.push_back(it.d.g_cs);
+          cco.push_back(it.d.g_co);
+          cC.push_back(it.d.Cout);
+          cnp.push_back(npix);
+          cout_.push_back(it.dbias);
+          cacc.push_back(it.d.accumulate);
+          calpha.push_back(it.d.alpha);
+          cshuf.push_back(it.d.shuffle);
+        } else {
+          int rc = srb_colsum_launch(ctx, it.gy, it.d.g_cs, it.d.g_co, it.d.Cout, npix, it.d.dtype, it.dbias,
+                                     it.d.accumulate, it.d.alpha, it.d.shuffle, st);
+          if (rc) return rc;
+        }
       }
     } else {
       int rc = srb_conv_wgrad(ctx, &it.d, it.x, it.gy, it.dw, it.dbias, stream);
       if (rc) return rc;
     }
+  }
+  if (!cx.empty()) {
+    int rc = srb_colsum_batched_launch(ctx, (int)cx.size(), cx.data(), ccs.data(), cco.data(), cC.data(), cnp.data(),
+                                       cout_.data(), cacc.data(), calpha.data(), cshuf.data(), st);
+    if (rc) return rc;
   }
   if (descs.empty()) return 0;
   return srb_wgrad_umma_batched(ctx, descs.data(), xs.data(), gys.data(), dws.data(), (int)descs.size(), st);

@@ -457,6 +457,44 @@ def test_conv_wgrad_batched_deferred():
         assert _rel(dw, rw)[0] < 1e-5 and _rel(db, rb)[0] < 1e-5
 
 
+def test_deferred_bias_grads_share_one_launch():
+    """Bias gradients of a deferred batch go through colsum_batched_kernel (one launch): channel
+    slices, the un-shuffled (i,j,c') channel order of PixelShuffle convs, accumulate and alpha,
+    checked against torch sums of the same bf16 tensors."""
+    from srb200 import lib as L, ops
+    g = torch.Generator().manual_seed(11)
+    dev = _dev()
+    cases = [  # (cout, g_cs, g_co, hw, shuffle, accumulate, alpha)
+        (64, 64, 0, 48, 0, False, 1.0),
+        (64, 192, 64, 24, 0, True, 0.5),
+        (256, 256, 0, 16, 2, False, 1.0),
+        (128, 128, 0, 20, 0, True, 1.0),
+        (32, 256, 96, 16, 0, False, 1.0),
+    ]
+    keep, want, got = [], [], []
+    c0 = L.launch_count()
+    with ops.deferred_wgrads():
+        for cout, g_cs, g_co, hw, shuffle, acc, alpha in cases:
+            x = torch.randn(2, hw, hw, 64, generator=g).to(torch.bfloat16).to(dev)
+            gy = torch.randn(2, hw, hw, g_cs, generator=g).to(torch.bfloat16).to(dev)
+            dw = torch.zeros(cout, 64, 3, 3, device=dev)
+            base = torch.randn(cout, generator=g).to(dev)
+            db = base.clone() if acc else torch.full((cout,), 7.0, device=dev)
+            ops.conv_wgrad(x, 0, 64, gy, g_co, cout, 3, dw, db, accumulate=acc, shuffle=shuffle, alpha=alpha)
+            sums = gy[..., g_co:g_co + cout].double().sum(dim=(0, 1, 2))
+            if shuffle:      # stored order (i*r+j)*C' + c'  ->  parameter order c'*r*r + (i*r+j)
+                rr = shuffle * shuffle
+                sums = sums.view(rr, cout // rr).t().reshape(-1)
+            want.append(sums * alpha + (base.double() if acc else 0))
+            got.append(db)
+            keep.append((x, gy, dw))
+    torch.cuda.synchronize()
+    n_launch = L.launch_count() - c0
+    for w_, g_ in zip(want, got):
+        assert _rel(g_, w_)[0] < 1e-5
+    assert n_launch <= 3, n_launch     # one column-sum launch + the batched weight-gradient launch(es)
+
+
 @pytest.mark.parametrize("shape", [(64, 64, 3), (256, 64, 3), (64, 576, 1), (64, 40, 3), (3, 64, 3), (64, 3, 3)])
 def test_pack_table_matches_pack_weight(shape):
     """srb_pack_table (one launch re-packing many weights, used once per optimizer step) must write
