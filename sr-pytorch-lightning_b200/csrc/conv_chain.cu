@@ -107,21 +107,6 @@ enum { TR_DEP = 0, TR_AFULL, TR_ISSUED, TR_ACC, TR_STAGED, TR_STORED, TR_RELEASE
 __device__ __forceinline__ int ref_space(uint16_t r) { return r >> 14; }
 __device__ __forceinline__ int ref_slot(uint16_t r) { return r & 0x3FFF; }
 
-// butterfly transpose-reduce over the 32 lanes of a warp: lane l ends with sum over lanes of s[l]
-__device__ __forceinline__ float warp_colsum32(float (&s)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float send = upper ? s[i] : s[i + off];
-      const float keep = upper ? s[i + off] : s[i];
-      s[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return s[0];
-}
-
 // 36 MMAs of one 128-pixel tile: D[tmem_d] = sum over the nine taps (kw slab, kh) and four 16-channel
 // k-steps of window(kh, kw) x filter(kw, kh).  first: the filter slabs of this op are awaited slab by
 // slab; last: each slab is handed back to the filter producer once its MMAs have been issued.
@@ -155,7 +140,7 @@ __device__ __forceinline__ void mma_tile(uint32_t tmem_d, uint32_t a_lo, uint32_
 // back from shared memory: warp q sums its 32 rows; lane = (chunk k = lane & 7, row phase lane >> 3), eight
 // conflict-free 16-byte loads per lane, two shuffle levels; lanes 0-7 then hold channels 8k..8k+7 and write
 // them to out[64].  Used AFTER the tile's TMA store has been issued, i.e. off the op's critical path
-// (a butterfly over the epilogue registers costs ~1 us before the store).
+// (a butterfly transpose-reduce over the epilogue registers cost ~1 us per tile).
 __device__ __forceinline__ void tile_colsum_lds(uint32_t tile, int q, int lane, float* out) {
   const int k = lane & 7, rp = lane >> 3;
   float a[8];
@@ -167,6 +152,36 @@ __device__ __forceinline__ void tile_colsum_lds(uint32_t tile, int q, int lane, 
     const uint4 v = ptx::lds128(tile + (uint32_t)r * 128u + (uint32_t)((k ^ (r & 7)) << 4));
     const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y), f2 = unpack_bf16x2(v.z), f3 = unpack_bf16x2(v.w);
     a[0] += f0.x; a[1] += f0.y; a[2] += f1.x; a[3] += f1.y; a[4] += f2.x; a[5] += f2.y; a[6] += f3.x; a[7] += f3.y;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a[j] += __shfl_xor_sync(0xffffffffu, a[j], 8);
+    a[j] += __shfl_xor_sync(0xffffffffu, a[j], 16);
+  }
+  if (rp == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[k * 8 + j] = a[j];
+  }
+}
+
+// Same access pattern over TWO staged tiles: column sums of the element-wise product (CALayer backward:
+// sum over pixels of g * t per channel).  Out-of-image rows are zero in both tiles (TMA zero fill / the
+// epilogue stages zeros), so no validity mask is needed.
+__device__ __forceinline__ void tile_prod_colsum_lds(uint32_t tile_a, uint32_t tile_b, int q, int lane, float* out) {
+  const int k = lane & 7, rp = lane >> 3;
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = q * 32 + rp + 4 * i;
+    const uint32_t off = (uint32_t)r * 128u + (uint32_t)((k ^ (r & 7)) << 4);
+    const uint4 u = ptx::lds128(tile_a + off);
+    const uint4 v = ptx::lds128(tile_b + off);
+    const float2 u0 = unpack_bf16x2(u.x), u1 = unpack_bf16x2(u.y), u2 = unpack_bf16x2(u.z), u3 = unpack_bf16x2(u.w);
+    const float2 v0 = unpack_bf16x2(v.x), v1 = unpack_bf16x2(v.y), v2 = unpack_bf16x2(v.z), v3 = unpack_bf16x2(v.w);
+    a[0] = fmaf(u0.x, v0.x, a[0]); a[1] = fmaf(u0.y, v0.y, a[1]); a[2] = fmaf(u1.x, v1.x, a[2]); a[3] = fmaf(u1.y, v1.y, a[3]);
+    a[4] = fmaf(u2.x, v2.x, a[4]); a[5] = fmaf(u2.y, v2.y, a[5]); a[6] = fmaf(u3.x, v3.x, a[6]); a[7] = fmaf(u3.y, v3.y, a[7]);
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -377,24 +392,10 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
         // CALayer + skip backward on one tile (rcan.py:10-29,54): g_row / t_row = this thread's 128-byte rows
         // of dL/dout and of the saved pre-attention tensor; dt = g*gate + ds/HW is written to out_row.
         auto ca_bwd_tile = [&](const uint32_t g_row, const uint32_t t_row, const uint32_t out_row) {
-#pragma unroll 1
-          for (int c0 = 0; c0 < 64; c0 += 32) {
-            float s[32];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint32_t off = (((uint32_t)(c0 >> 3) + g) ^ sw) << 4;
-              const uint4 tv = ptx::lds128(t_row + off);
-              const uint4 gv = ptx::lds128(g_row + off);
-              const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 ft = unpack_bf16x2(tw[e]), fg = unpack_bf16x2(gw[e]);
-                s[g * 8 + e * 2] = ft.x * fg.x;
-                s[g * 8 + e * 2 + 1] = ft.y * fg.y;
-              }
-            }
-            colsum_s[c][q][c0 + lane] = warp_colsum32(s, lane);      // out-of-image rows are zero-filled by TMA
-          }
+          // sum over this warp's 32 pixels of g*t per channel, read back from the two staged tiles (eight
+          // conflict-free 16-byte loads per tile and lane + two shuffle levels; the register butterfly this
+          // replaces was ~250 instructions per thread on the critical path of every RCAB)
+          tile_prod_colsum_lds(g_row - (uint32_t)row * 128u, t_row - (uint32_t)row * 128u, q, lane, colsum_s[c][q]);
           ptx::named_bar_sync(bar_id, 128);
           if (row < 64) {
             const float tot = (colsum_s[c][0][row] + colsum_s[c][1][row]) + (colsum_s[c][2][row] + colsum_s[c][3][row]);
@@ -593,19 +594,6 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
               for (int g = 0; g < 4; ++g)
                 ptx::sts128(orow + ((((uint32_t)(c0 >> 3) + g) ^ sw) << 4),
                             make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]));
-              if ((fl & SRB_COLSUM) && (fl & SRB_CHAIN_CA)) {
-                // CALayer pool (needed before anything else can happen): sums of the STORED (bf16-rounded)
-                // values over this warp's 32 pixels; the four warps' partial sums meet in shared memory so
-                // that a tile issues 64 atomics, not 256.  Other column sums are taken after the store.
-                float s[32];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const float2 f = unpack_bf16x2(packed[i]);
-                  s[2 * i] = f.x;
-                  s[2 * i + 1] = f.y;
-                }
-                colsum_s[c][q][c0 + lane] = warp_colsum32(s, lane);
-              }
             }
           };
           switch ((flags & 47u) | (o.scale != 1.f ? kScaled : 0u)) {
@@ -624,6 +612,11 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
           ptx::fence_proxy_async_smem();
           ptx::named_bar_sync(bar_id, 128);
           if (ca) {
+            // CALayer pool (needed before anything else can happen): sums of the STORED (bf16-rounded) values,
+            // read back from the staged tile (the register butterfly this replaces cost ~1 us per tile); the
+            // four warps' partial sums meet in shared memory so that a tile issues 64 atomics, not 256
+            tile_colsum_lds(stg, q, lane, colsum_s[c][q]);
+            ptx::named_bar_sync(bar_id, 128);
             if (row < 64) {
               const float tot = (colsum_s[c][0][row] + colsum_s[c][1][row]) + (colsum_s[c][2][row] + colsum_s[c][3][row]);
               atomicAdd(o.colsum + (int64_t)n * 64 + row, tot);
