@@ -391,7 +391,7 @@ def run_ours(args):
                                "launch, timed alone over graph replays of 10 rotating arena sets (2.9 GB > L2)",
                      "us_per_launch": k_us, "us_forward_launch": k_us_f, "us_backward_launch": k_us_b,
                      "flop_per_launch": k_flop, "launches_per_step": 20,
-                     "share_of_step": 10.0 * (k_us_f + k_us_b) / (ms_step * 1e3),
+                     "share_of_step": (10.0 * (k_us_f + k_us_b) / (ms_step * 1e3)) if args.model == "rcan" else None,
                      "traffic_note": "dram__bytes_read+write per launch from profiles/r01_ncu_conv_chain_v4.txt",
                      "peak_source": peaks["source"]},
         "roofline_step": {"bound": "tensor", "achieved": step_tflops, "peak": peaks["sustained"], "unit": "TFLOP/s",

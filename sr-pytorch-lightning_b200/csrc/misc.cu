@@ -311,9 +311,41 @@ __global__ void relu_bwd_kernel(const T* __restrict__ g, int g_cs, int g_co, con
   }
 }
 
+// bf16, 8 channels (16 bytes) per thread: the RDN dense-block backward masks a 64-channel slice of the
+// 576-channel gradient buffer per layer (128 launches per step; the scalar form took 11.5 us each)
+__global__ void relu_bwd_vec8_kernel(const __nv_bfloat16* __restrict__ g, int g_cs, int g_co,
+                                     const __nv_bfloat16* __restrict__ act, int a_cs, int a_co,
+                                     __nv_bfloat16* __restrict__ out, int o_cs, int o_co, int vpp, int64_t nvec) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  const int64_t p = i / vpp;
+  const int c = (int)(i - p * vpp) * 8;
+  const uint4 a = *reinterpret_cast<const uint4*>(act + p * a_cs + a_co + c);
+  uint4 v = *reinterpret_cast<const uint4*>(g + p * g_cs + g_co + c);
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+  uint32_t vw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = unpack_bf16x2(aw[e]);
+    if (!(f.x > 0.f)) vw[e] &= 0xFFFF0000u;
+    if (!(f.y > 0.f)) vw[e] &= 0x0000FFFFu;
+  }
+  *reinterpret_cast<uint4*>(out + p * o_cs + o_co + c) = make_uint4(vw[0], vw[1], vw[2], vw[3]);
+}
+
 extern "C" int srb_relu_bwd(srb_ctx* ctx, const void* g, int g_cs, int g_co, const void* act, int a_cs, int a_co,
                             void* out, int o_cs, int o_co, int C, int64_t npix, int dtype, void* stream) {
   SRB_REQUIRE(ctx && g && act && out, "srb_relu_bwd: null argument");
+  if (dtype == SRB_BF16 && C % 8 == 0 && !((g_cs | g_co | a_cs | a_co | o_cs | o_co) % 8) &&
+      !((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(act) | reinterpret_cast<uintptr_t>(out)) & 15)) {
+    const int vpp = C / 8;
+    const int64_t nvec = npix * vpp;
+    if (nvec == 0) return 0;
+    relu_bwd_vec8_kernel<<<srb_cdiv(nvec, 256), 256, 0, S(stream)>>>(
+        (const __nv_bfloat16*)g, g_cs, g_co, (const __nv_bfloat16*)act, a_cs, a_co, (__nv_bfloat16*)out, o_cs, o_co, vpp, nvec);
+    SRB_LAUNCH_CHECK();
+    return 0;
+  }
   int64_t total = npix * C;
   int blocks = srb_cdiv(total, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -374,33 +406,42 @@ int srb_colsum_launch(srb_ctx* ctx, const void* x, int cs, int co, int C, int64_
   return 0;
 }
 
-// Many bias gradients in ONE launch (the deferred weight-gradient batch, conv.cu): blockIdx.y = item,
-// a thread reads 8 bf16 channels per 16-byte load, C/8 threads cover a pixel, 256/(C/8) pixels per
-// CTA iteration; partial sums meet in shared memory and leave as C atomics per CTA.  (One
-// colsum_kernel launch per bias was 15 x 14.7 us of the RCAN step, scalar 2-byte loads.)
+// Many bias gradients in ONE launch (the deferred weight-gradient batch, conv.cu).  A CTA owns one
+// 128 KB chunk of one item (flat grid over all chunks, so a 96x96x256 gradient gets 16x the CTAs of a
+// 48x48x64 one); a thread reads 8 bf16 channels per 16-byte load, C/8 threads cover a pixel,
+// 256/(C/8) pixels per iteration, four loads in flight; partial sums meet in shared memory and leave
+// as C atomics per CTA.  (One colsum_kernel launch per bias was 15 x 14.7 us of the RCAN step.)
 struct ColsumItem {
   const __nv_bfloat16* x;
   float* out;
   int64_t npix;
   int cs, co, C, shuffle;
   float alpha;
+  int first_block, ppc;        // first CTA of this item, pixels per CTA
 };
 constexpr int kColsumMaxItems = 64;
+constexpr int kColsumChunkBytes = 128 * 1024;
 struct ColsumBatch {
   ColsumItem it[kColsumMaxItems];
+  int n;
 };
 
 __global__ void __launch_bounds__(256) colsum_batched_kernel(const __grid_constant__ ColsumBatch B) {
   __shared__ float red[256][9];
-  const ColsumItem& it = B.it[blockIdx.y];
+  int ii = 0;
+  while (ii + 1 < B.n && (int)blockIdx.x >= B.it[ii + 1].first_block) ++ii;
+  const ColsumItem& it = B.it[ii];
   const int vpp = it.C >> 3;                 // 16-byte vectors per pixel (power of two, <= 32)
   const int ppi = 256 / vpp;                 // pixels per CTA iteration
   const int v = threadIdx.x % vpp, pl = threadIdx.x / vpp;
+  const int64_t p0 = (int64_t)((int)blockIdx.x - it.first_block) * it.ppc;
+  const int64_t p1 = p0 + it.ppc < it.npix ? p0 + it.ppc : it.npix;
   float a[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] = 0.f;
   const __nv_bfloat16* base = it.x + it.co + v * 8;
-  for (int64_t p = (int64_t)blockIdx.x * ppi + pl; p < it.npix; p += (int64_t)gridDim.x * ppi) {
+#pragma unroll 4
+  for (int64_t p = p0 + pl; p < p1; p += ppi) {
     const uint4 q = __ldg(reinterpret_cast<const uint4*>(base + p * it.cs));
     const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
     a[0] += f0.x; a[1] += f0.y; a[2] += f1.x; a[3] += f1.y; a[4] += f2.x; a[5] += f2.y; a[6] += f3.x; a[7] += f3.y;
@@ -437,24 +478,25 @@ int srb_colsum_batched_launch(srb_ctx* ctx, int n, const void* const* xs, const 
   for (int i0 = 0; i0 < n; i0 += kColsumMaxItems) {
     const int m = n - i0 < kColsumMaxItems ? n - i0 : kColsumMaxItems;
     ColsumBatch B;
-    int64_t max_npix = 1;
+    int blocks = 0;
     for (int i = 0; i < m; ++i) {
       const int k = i0 + i;
       if (!accumulate[k]) SRB_CHECK_CUDA(cudaMemsetAsync(outs[k], 0, sizeof(float) * C[k], st));
-      B.it[i].x = reinterpret_cast<const __nv_bfloat16*>(xs[k]);
-      B.it[i].out = outs[k];
-      B.it[i].npix = npix[k];
-      B.it[i].cs = cs[k];
-      B.it[i].co = co[k];
-      B.it[i].C = C[k];
-      B.it[i].shuffle = shuffle[k];
-      B.it[i].alpha = alpha[k];
-      if (npix[k] > max_npix) max_npix = npix[k];
+      ColsumItem& it = B.it[i];
+      it.x = reinterpret_cast<const __nv_bfloat16*>(xs[k]);
+      it.out = outs[k];
+      it.npix = npix[k];
+      it.cs = cs[k];
+      it.co = co[k];
+      it.C = C[k];
+      it.shuffle = shuffle[k];
+      it.alpha = alpha[k];
+      it.first_block = blocks;
+      it.ppc = kColsumChunkBytes / (C[k] * 2);      // a multiple of the 256 / (C/8) pixels of one iteration
+      blocks += srb_cdiv(npix[k] > 0 ? npix[k] : 1, it.ppc);
     }
-    int slabs = srb_cdiv(max_npix, 1024);
-    if (slabs > 64) slabs = 64;
-    if (slabs < 1) slabs = 1;
-    colsum_batched_kernel<<<dim3(slabs, m), 256, 0, st>>>(B);
+    B.n = m;
+    colsum_batched_kernel<<<blocks, 256, 0, st>>>(B);
     SRB_LAUNCH_CHECK();
   }
   return 0;

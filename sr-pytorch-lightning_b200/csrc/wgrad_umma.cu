@@ -18,6 +18,7 @@
 // whole reduction per CTA there is no split-K traffic at all, and 148 CTAs stay busy even though
 // one layer's dW is only 64x64x9.  The backward pass defers its weight gradients into such batches
 // (srb200/functional.py WgradQueue): they are off the critical path of the dgrad chain.
+#include <stdlib.h>
 #include <vector>
 
 #include "common.cuh"
@@ -31,6 +32,16 @@ constexpr int kTW = 8, kTH = 16;    // 128-pixel tile, 8 wide (one swizzle atom 
 constexpr int kABytes = (kTH + 2) * kTW * 128;   // one kw-shifted input window (18 rows)
 constexpr int kGBytes = kTH * kTW * 128;         // gradient tile
 constexpr int kStageBytes = 3 * kABytes + kGBytes;
+// Experimental single-window variant (SRB200_WGRAD_ONEWIN=1): ONE (8+2)-pixel-wide window per tile serves all
+// three kw shifts (tap (kh,kw) starts (kh*10+kw)*128 bytes into it; 8-pixel K groups are one 1280-byte
+// window row apart), 39 KB per stage instead of 71 KB -> five stages and 45 % less TMA traffic.  Relies on
+// the swizzle being a function of the absolute shared-memory address for MN-major operands too (shown for
+// K-major operands by profiles/r01_hw_probes.txt P1); off until the parity tests have passed with it on.
+constexpr int kPW = kTW + 2;
+constexpr int kWinBytes1 = 23 * 1024;            // 18 x 10 x 128 = 23040, padded so that the G tile stays 1024-aligned
+constexpr int kWinTx1 = (kTH + 2) * kPW * 128;
+constexpr int kStageBytes1 = kWinBytes1 + kGBytes;
+constexpr int kStages1 = 5;
 constexpr int kMaxBlocks = 74;      // blocks per launch (kernel-parameter space: 74 x 320 B < 32 KB)
 constexpr uint32_t kTmemCols = 512; // 5 accumulators x 64 columns -> next power of two
 
@@ -43,7 +54,8 @@ struct alignas(64) WgradBlock {
   int Cin, Cout;        // layer sizes (dW strides, shuffle mapping)
   int tiles_w, tiles_h, ntiles;
   int shuffle;
-  int rmw;              // 1: dw += (non-atomic, S == 1 and accumulate)
+  int16_t rmw;          // 1: dw += (non-atomic, S == 1 and accumulate)
+  int16_t k1;           // 1: 1x1 layer (RDN LFF / GFF, rdn.py:37,70): only the centre tap exists
   float alpha;
   int cta0, S;          // this block is processed by CTAs [cta0, cta0 + S) of the launch, each
                         // taking every S-th pixel tile (S proportional to the block's tile count)
@@ -54,7 +66,10 @@ struct WgradParams {
   int nblocks;
 };
 
+template <bool OW>
 __global__ void __launch_bounds__(kThreads, 1) wgrad_umma_kernel(const __grid_constant__ WgradParams P) {
+  constexpr int kStages = OW ? kStages1 : ::kStages;
+  constexpr int kStageBytes = OW ? kStageBytes1 : ::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kStages];
   __shared__ uint64_t empty_bar[kStages];
@@ -98,12 +113,19 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_umma_kernel(const __grid_co
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
         ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
-        ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)kStageBytes);
         const uint32_t base = ring + (uint32_t)s * kStageBytes;
+        if constexpr (OW) {
+          ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(kWinTx1 + kGBytes));
+          ptx::tma_load_4d(base, &B.tmX, &full_bar[s], B.xc0, w0 - 1, h0 - 1, n);
+          ptx::tma_load_4d(base + kWinBytes1, &B.tmG, &full_bar[s], B.gc0, w0, h0, n);
+        } else {
+          ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(B.k1 ? kABytes + kGBytes : kStageBytes));
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw)
-          ptx::tma_load_4d(base + kw * kABytes, &B.tmX, &full_bar[s], B.xc0, w0 + kw - 1, h0 - 1, n);
-        ptx::tma_load_4d(base + 3 * kABytes, &B.tmG, &full_bar[s], B.gc0, w0, h0, n);
+          for (int kw = 0; kw < 3; ++kw)
+            if (!B.k1 || kw == 1)
+              ptx::tma_load_4d(base + kw * kABytes, &B.tmX, &full_bar[s], B.xc0, w0 + kw - 1, h0 - 1, n);
+          ptx::tma_load_4d(base + 3 * kABytes, &B.tmG, &full_bar[s], B.gc0, w0, h0, n);
+        }
       }
     }
   } else if (warp == 1) {
@@ -116,7 +138,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_umma_kernel(const __grid_co
         ptx::mbar_wait(&full_bar[s], ph);
         ptx::tc_fence_after();
         const uint32_t base = ring + (uint32_t)s * kStageBytes;
-        const uint32_t gbase = base + 3 * kABytes;
+        const uint32_t gbase = base + (OW ? kWinBytes1 : 3 * kABytes);
         // accumulator a: two taps stacked along M.  a<3: (kh0,kw=a)+(kh1,kw=a), second atom one
         // tile row (1024 B) further; a=3: (kh2,kw0)+(kh2,kw1), second atom in the next window;
         // a=4: (kh2,kw2) + don't-care rows (upper 64 lanes are discarded by the epilogue)
@@ -125,12 +147,25 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_umma_kernel(const __grid_co
         const uint32_t acc_flag = (uint32_t)(it != 0);
 #pragma unroll
         for (int a = 0; a < 5; ++a) {
-          const uint32_t a0 = a < 3 ? base + a * kABytes : (a == 3 ? base + 2 * kTW * 128 : base + 2 * kABytes + 2 * kTW * 128);
-          const uint32_t a_lo = ptx::smem_desc_lo(a0, a == 3 ? (uint32_t)kABytes : 1024u);
+          if (B.k1 && a != 1) continue;   // 1x1: the centre tap is the upper half of accumulator 1
+          if constexpr (OW) {
+            // tap (kh, kw) starts at window pixel (kh, kw); second tap of the pair: next row (a < 3, a = 4's
+            // discarded half) or next pixel (a = 3); K groups of 8 pixels are one window row (1280 B) apart
+            constexpr uint32_t hi1 = ptx::smem_desc_hi_sw128((uint32_t)kPW * 128u);
+            const uint32_t a0 = base + (uint32_t)((a < 3 ? a : (a == 3 ? 2 * kPW : 2 * kPW + 2)) * 128);
+            const uint32_t a_lo = ptx::smem_desc_lo(a0, a == 3 ? 128u : (uint32_t)kPW * 128u);
 #pragma unroll
-          for (int j = 0; j < 8; ++j)   // 8 x 16 pixels
-            ptx::umma_bf16_lohi(tmem_acc + (uint32_t)a * 64u, a_lo + j * 128u, hi, g_lo + j * 128u, hi, idesc,
-                                j != 0 ? 1u : acc_flag);
+            for (int j = 0; j < 8; ++j)   // 8 x 16 pixels = 8 x two window rows
+              ptx::umma_bf16_lohi(tmem_acc + (uint32_t)a * 64u, a_lo + j * (2u * kPW * 128u / 16u), hi1, g_lo + j * 128u, hi,
+                                  idesc, j != 0 ? 1u : acc_flag);
+          } else {
+            const uint32_t a0 = a < 3 ? base + a * kABytes : (a == 3 ? base + 2 * kTW * 128 : base + 2 * kABytes + 2 * kTW * 128);
+            const uint32_t a_lo = ptx::smem_desc_lo(a0, a == 3 ? (uint32_t)kABytes : 1024u);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)   // 8 x 16 pixels
+              ptx::umma_bf16_lohi(tmem_acc + (uint32_t)a * 64u, a_lo + j * 128u, hi, g_lo + j * 128u, hi, idesc,
+                                  j != 0 ? 1u : acc_flag);
+          }
         }
         ptx::umma_commit(&empty_bar[s]);
       }
@@ -146,11 +181,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_umma_kernel(const __grid_co
     ptx::tc_fence_after();
 #pragma unroll 1
     for (int a = 0; a < 5; ++a) {
+      if (B.k1 && a != 1) continue;
       int kh, kw;
       if (a < 3) { kh = half; kw = a; }
       else if (a == 3) { kh = 2; kw = half; }
       else { kh = 2; kw = 2; }
-      const bool live = !(a == 4 && half == 1) && ci < B.Cin;
+      const bool live = !(a == 4 && half == 1) && ci < B.Cin && !(B.k1 && half == 0);
 #pragma unroll 1
       for (int c0 = 0; c0 < 64; c0 += 32) {
         uint32_t acc[32];
@@ -162,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_umma_kernel(const __grid_co
             const int cop = B.co0 + c0 + j;                      // channel in gy's order
             if (cop >= B.Cout) continue;
             const int co = rr > 1 ? (cop % Cp) * rr + cop / Cp : cop;
-            float* dst = B.dw + (((int64_t)co * B.Cin + ci) * 3 + kh) * 3 + kw;
+            float* dst = B.k1 ? B.dw + (int64_t)co * B.Cin + ci : B.dw + (((int64_t)co * B.Cin + ci) * 3 + kh) * 3 + kw;
             const float v = __uint_as_float(acc[j]) * B.alpha;
             if (S > 1) atomicAdd(dst, v);       // split reduction (dW pre-zeroed or accumulated)
             else if (B.rmw) *dst += v;            // whole reduction here, gradient accumulation
@@ -186,10 +222,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int encode_act_map(srb_ctx* ctx, CUtensorMap* map, const void* base, int N, int H, int W, int cs, int cextent,
-                   int box_h) {
+                   int box_h, int box_w = kTW) {
   cuuint64_t dims[4] = {(cuuint64_t)cextent, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)cs * 2, (cuuint64_t)W * cs * 2, (cuuint64_t)H * W * cs * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)kTW, (cuuint32_t)box_h, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled);
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
@@ -205,7 +241,7 @@ int encode_act_map(srb_ctx* ctx, CUtensorMap* map, const void* base, int N, int 
 }  // namespace
 
 int srb_wgrad_umma_ok(const srb_wgrad_desc* d) {
-  if (d->dtype != SRB_BF16 || d->ksize != 3) return 0;
+  if (d->dtype != SRB_BF16 || (d->ksize != 3 && d->ksize != 1)) return 0;
   if (d->Cin < 1 || d->Cout < 1) return 0;   // partial 64-channel blocks: TMA zero-fills, epilogue clips
   if (d->x_cs % 8 || d->x_co % 8 || d->g_cs % 8 || d->g_co % 8) return 0;
   if (d->W < 8) return 0;
@@ -217,16 +253,23 @@ int srb_wgrad_umma_ok(const srb_wgrad_desc* d) {
 int srb_wgrad_umma_batched(srb_ctx* ctx, const srb_wgrad_desc* descs, const void* const* xs, const void* const* gys,
                            float* const* dws, int n_items, cudaStream_t st) {
   static bool attr_set = false;
-  const size_t smem = (size_t)kStages * kStageBytes + 1024;
+  static const bool one_win = [] {
+    const char* e = getenv("SRB200_WGRAD_ONEWIN");
+    return e && e[0] && e[0] != '0';
+  }();
+  const size_t smem = (one_win ? (size_t)kStages1 * kStageBytes1 : (size_t)kStages * kStageBytes) + 1024;
   if (!attr_set) {
-    SRB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SRB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)((size_t)kStages * kStageBytes + 1024)));
+    SRB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)((size_t)kStages1 * kStageBytes1 + 1024)));
     attr_set = true;
   }
   std::vector<WgradBlock> blocks;
   for (int i = 0; i < n_items; ++i) {
     const srb_wgrad_desc& d = descs[i];
     CUtensorMap tmX, tmG;  // one pair per layer; its 64x64 blocks differ by channel coordinates only
-    int rc = encode_act_map(ctx, &tmX, xs[i], d.N, d.H, d.W, d.x_cs, d.x_co + d.Cin, kTH + 2);
+    int rc = encode_act_map(ctx, &tmX, xs[i], d.N, d.H, d.W, d.x_cs, d.x_co + d.Cin, kTH + 2, one_win ? kPW : kTW);
     if (rc) return rc;
     rc = encode_act_map(ctx, &tmG, gys[i], d.N, d.H, d.W, d.g_cs, d.g_co + d.Cout, kTH);
     if (rc) return rc;
@@ -248,6 +291,7 @@ int srb_wgrad_umma_batched(srb_ctx* ctx, const srb_wgrad_desc* descs, const void
         B.ntiles = d.N * tiles_w * tiles_h;
         B.shuffle = d.shuffle;
         B.rmw = d.accumulate ? 1 : 0;
+        B.k1 = d.ksize == 1 ? 1 : 0;
         B.alpha = d.alpha;
         blocks.push_back(B);
       }
@@ -282,7 +326,7 @@ int srb_wgrad_umma_batched(srb_ctx* ctx, const srb_wgrad_desc* descs, const void
     // split reductions add into dW with red.global.add, so overwritten layers start from zero
     for (int i = 0; i < n_items; ++i)
       if (!descs[i].accumulate)
-        SRB_CHECK_CUDA(cudaMemsetAsync(dws[i], 0, sizeof(float) * (size_t)descs[i].Cout * descs[i].Cin * 9, st));
+        SRB_CHECK_CUDA(cudaMemsetAsync(dws[i], 0, sizeof(float) * (size_t)descs[i].Cout * descs[i].Cin * descs[i].ksize * descs[i].ksize, st));
     for (auto& B : blocks) B.rmw = 1;
   }
   WgradParams* P = new WgradParams();
@@ -293,7 +337,8 @@ int srb_wgrad_umma_batched(srb_ctx* ctx, const srb_wgrad_desc* descs, const void
     for (int b = 0; b < nb; ++b) P->blk[b] = blocks[b0 + b];
     P->nblocks = nb;
     const int ctas = P->blk[nb - 1].cta0 + P->blk[nb - 1].S;
-    wgrad_umma_kernel<<<ctas, kThreads, smem, st>>>(*P);
+    if (one_win) wgrad_umma_kernel<true><<<ctas, kThreads, smem, st>>>(*P);
+    else wgrad_umma_kernel<false><<<ctas, kThreads, smem, st>>>(*P);
     __atomic_fetch_add(&g_srb_launches, 1ull, __ATOMIC_RELAXED);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -314,6 +314,16 @@ def test_layout_and_elementwise():
         o2 = torch.empty_like(a)
         ops.relu_bwd(a, 0, m, 0, o2, 0, 24)
         assert torch.equal(o2, torch.where(m > 0, a, torch.zeros_like(a)))
+        # channel slices, in place (the RDN dense-block backward masks one 64-channel slice per layer);
+        # zeros and negative zeros in the activation both mask
+        gd = torch.randn(2, 5, 6, 40, generator=g).to(dt).to(dev)
+        act = torch.randn(2, 5, 6, 40, generator=g).to(dt).to(dev)
+        act[0, 0, 0, 8:12] = 0.0
+        act[0, 0, 1, 8:12] = -0.0
+        keep = gd.clone()
+        ops.relu_bwd(gd, 8, act, 8, gd, 8, 16)
+        assert torch.equal(gd[..., 8:24], torch.where(act[..., 8:24] > 0, keep[..., 8:24], torch.zeros_like(keep[..., 8:24])))
+        assert torch.equal(gd[..., :8], keep[..., :8]) and torch.equal(gd[..., 24:], keep[..., 24:])
         gsh = torch.randn(2, 8, 12, 5, generator=g).to(dt).to(dev)
         un = ops.pixel_unshuffle(gsh, 2)
         ref = F.pixel_unshuffle(gsh.permute(0, 3, 1, 2).float(), 2)         # channels (c', i, j)
@@ -385,6 +395,9 @@ WGRAD_UMMA_CASES = [
     dict(n=2, h=16, w=16, cin=3, cout=64, x_cs=8),                 # head conv (partial ci block)
     dict(n=1, h=32, w=24, cin=64, cout=3, g_cs=8),                 # tail conv (partial co block)
     dict(n=1, h=16, w=16, cin=96, cout=32, x_cs=256, g_cs=256, g_co=96),   # RDN-A dense layer
+    dict(n=2, h=48, w=48, cin=576, cout=64, k=1),                  # RDN LFF (1x1: centre tap only)
+    dict(n=1, h=20, w=13, cin=1024, cout=64, k=1),                 # RDN GFF.0, ragged tiles
+    dict(n=1, h=16, w=16, cin=64, cout=64, k=1, x_cs=192, x_co=64, alpha=0.5, accumulate=True),
 ]
 
 
@@ -398,19 +411,20 @@ def test_conv_wgrad_umma(case):
     shuffle, alpha, accumulate = c.get("shuffle", 0), c.get("alpha", 1.0), c.get("accumulate", False)
     x_cs, x_co = c.get("x_cs", cin), c.get("x_co", 0)
     g_cs, g_co = c.get("g_cs", cout), c.get("g_co", 0)
+    k = c.get("k", 3)
     g = torch.Generator().manual_seed(6)
     xfull = torch.randn(n, h, w, x_cs, generator=g).to(torch.bfloat16)
     r = shuffle if shuffle else 1
     gy = torch.randn(n, h * r, w * r, cout // (r * r), generator=g).to(torch.bfloat16)
-    wt = torch.zeros(cout, cin, 3, 3, dtype=torch.float64, requires_grad=True)
+    wt = torch.zeros(cout, cin, k, k, dtype=torch.float64, requires_grad=True)
     bt = torch.zeros(cout, dtype=torch.float64, requires_grad=True)
-    y = F.conv2d(_nchw(xfull[..., x_co:x_co + cin].double()), wt, bt, padding=1)
+    y = F.conv2d(_nchw(xfull[..., x_co:x_co + cin].double()), wt, bt, padding=k // 2)
     if shuffle:
         y = F.pixel_shuffle(y, r)
     y.backward(_nchw(gy.double()))
     dev = _dev()
-    base = torch.randn(cout, cin, 3, 3, generator=g)
-    dw = base.to(dev).clone() if accumulate else torch.full((cout, cin, 3, 3), 3.0, device=dev)
+    base = torch.randn(cout, cin, k, k, generator=g)
+    dw = base.to(dev).clone() if accumulate else torch.full((cout, cin, k, k), 3.0, device=dev)
     db = torch.zeros(cout, device=dev) if accumulate else torch.full((cout,), 3.0, device=dev)
     gyd = gy.to(dev)
     if shuffle:
@@ -419,7 +433,7 @@ def test_conv_wgrad_umma(case):
         gfull = torch.randn(n, h, w, g_cs, generator=g).to(torch.bfloat16).to(dev)
         gfull[..., g_co:g_co + cout] = gyd
         gyd = gfull
-    ops.conv_wgrad(xfull.to(dev), x_co, cin, gyd, g_co, cout, 3, dw, db, accumulate=accumulate, shuffle=shuffle,
+    ops.conv_wgrad(xfull.to(dev), x_co, cin, gyd, g_co, cout, k, dw, db, accumulate=accumulate, shuffle=shuffle,
                    alpha=alpha, backend=L.BACKEND_UMMA)
     torch.cuda.synchronize()
     want_w = wt.grad * alpha + (base.double() if accumulate else 0)
