@@ -32,11 +32,13 @@ constexpr int kTW = 8, kTH = 16;    // 128-pixel tile, 8 wide (one swizzle atom 
 constexpr int kABytes = (kTH + 2) * kTW * 128;   // one kw-shifted input window (18 rows)
 constexpr int kGBytes = kTH * kTW * 128;         // gradient tile
 constexpr int kStageBytes = 3 * kABytes + kGBytes;
-// Experimental single-window variant (SRB200_WGRAD_ONEWIN=1): ONE (8+2)-pixel-wide window per tile serves all
-// three kw shifts (tap (kh,kw) starts (kh*10+kw)*128 bytes into it; 8-pixel K groups are one 1280-byte
-// window row apart), 39 KB per stage instead of 71 KB -> five stages and 45 % less TMA traffic.  Relies on
-// the swizzle being a function of the absolute shared-memory address for MN-major operands too (shown for
-// K-major operands by profiles/r01_hw_probes.txt P1); off until the parity tests have passed with it on.
+// Single-window variant (default for batches of 3x3 layers; SRB200_WGRAD_ONEWIN=0 selects the three-window
+// form): ONE (8+2)-pixel-wide window per tile serves all three kw shifts (tap (kh,kw) starts (kh*10+kw)*128
+// bytes into it; 8-pixel K groups are one 1280-byte window row apart), 39 KB per stage instead of 71 KB ->
+// five stages and 45 % less TMA traffic.  The swizzle is a function of the absolute shared-memory address
+// for MN-major operands too (K-major: profiles/r01_hw_probes.txt P1; MN-major: the parity tests pass in
+// this mode).  Measured: RCAN step 8.58 -> 8.46 ms; a batch with 1x1 layers (RDN) keeps three windows —
+// a 1x1 block loads only the centre window there (18 KB instead of 23 KB) and was 2 % faster that way.
 constexpr int kPW = kTW + 2;
 constexpr int kWinBytes1 = 23 * 1024;            // 18 x 10 x 128 = 23040, padded so that the G tile stays 1024-aligned
 constexpr int kWinTx1 = (kTH + 2) * kPW * 128;
@@ -253,10 +255,13 @@ int srb_wgrad_umma_ok(const srb_wgrad_desc* d) {
 int srb_wgrad_umma_batched(srb_ctx* ctx, const srb_wgrad_desc* descs, const void* const* xs, const void* const* gys,
                            float* const* dws, int n_items, cudaStream_t st) {
   static bool attr_set = false;
-  static const bool one_win = [] {
+  static const bool one_win_enabled = [] {
     const char* e = getenv("SRB200_WGRAD_ONEWIN");
-    return e && e[0] && e[0] != '0';
+    return !(e && e[0] == '0');
   }();
+  bool one_win = one_win_enabled;
+  for (int i = 0; i < n_items; ++i)
+    if (descs[i].ksize == 1) one_win = false;
   const size_t smem = (one_win ? (size_t)kStages1 * kStageBytes1 : (size_t)kStages * kStageBytes) + 1024;
   if (!attr_set) {
     SRB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
