@@ -62,6 +62,11 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ int atom_add_acq_rel_gpu(int* p, int v) {
+  int old;
+  asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
 __device__ __forceinline__ void red_release_gpu(int* p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -201,6 +206,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
   __shared__ uint64_t a_full[2], a_empty[2], e_full[2], e_empty[2], e2_full[2], e2_empty[2], acc_full[2], acc_empty[2];
   __shared__ uint64_t g_full[2];   // deferred-gate ops: the epilogue warpgroup has rewritten the window in place
   __shared__ uint32_t tmem_slot;
+  __shared__ int last_s[2];        // POOL_OUT / PROD_OUT: this tile completed its sample's sums
   __shared__ __align__(16) float bias_s[2][64];
   __shared__ float colsum_s[2][4][64];
   __shared__ float ca_s[2][64], ca_y[2][64], ca_du[2][64], ca_ds[2][64], ca_z[2][kMaxCr], ca_dv[2][kMaxCr];
@@ -539,62 +545,32 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
           }
         };
 
-        // ---- deferred gate (GATE_IN / GATE_BWD_IN): the per-sample sums were published by op-1 ----
-        // forward: ca_y[c][ch] = sigmoid(W2 relu(W1 mean + b1) + b2) (rcan.py:17-28); mean / gate saved for backward
-        auto gate_fwd = [&](const int* cnt_pool) {
-          float w1a[2] = {0.f, 0.f}, w1b[2] = {0.f, 0.f}, b1v[2] = {0.f, 0.f};
-          {
-            int u = 0;
-            for (int jj = q; jj < Cr && u < 2; jj += 4, ++u) {
-              w1a[u] = __ldg(o.ca_w1 + jj * 64 + lane);
-              w1b[u] = __ldg(o.ca_w1 + jj * 64 + lane + 32);
-              b1v[u] = __ldg(o.ca_b1 + jj);
-            }
-          }
-          float w2r[4] = {0.f, 0.f, 0.f, 0.f}, b2v = 0.f;
-          if (row < 64) {
-            b2v = __ldg(o.ca_b2 + row);
-            for (int jj = 0; jj < Cr && jj < 4; ++jj) w2r[jj] = __ldg(o.ca_w2 + row * Cr + jj);
-          }
-          if (store_thread) {
-            wait_counter(cnt_pool, p.tiles_per_sample);
-            CH_TRACE(c, op, TR_POOL);
-          }
+        // ---- deferred gate: the tile that completes a sample's sums (POOL_OUT / PROD_OUT) evaluates the gate ONCE
+        // for the sample and publishes it; the tiles of the next op (GATE_IN / GATE_BWD_IN) only read 64 values ----
+        // forward: ca_y[n][ch] = sigmoid(W2 relu(W1 mean + b1) + b2) (rcan.py:17-28); mean / gate saved for backward
+        auto gate_fwd = [&]() {
+          if (row < 64) ca_s[c][row] = __ldcg(o.colsum + (int64_t)n * 64 + row) * inv_hw;
           ptx::named_bar_sync(bar_id, 128);
-          if (row < 64) ca_s[c][row] = __ldcg(o.pool_in + (int64_t)n * 64 + row) * inv_hw;
-          ptx::named_bar_sync(bar_id, 128);
-          {
-            int u = 0;
-            for (int jj = q; jj < Cr; jj += 4, ++u) {
-              float a = (u < 2 ? w1a[u] : __ldg(o.ca_w1 + jj * 64 + lane)) * ca_s[c][lane] +
-                        (u < 2 ? w1b[u] : __ldg(o.ca_w1 + jj * 64 + lane + 32)) * ca_s[c][lane + 32];
-              a = warp_sum(a);
-              if (lane == 0) ca_z[c][jj] = fmaxf(a + (u < 2 ? b1v[u] : __ldg(o.ca_b1 + jj)), 0.f);
-            }
+          for (int jj = q; jj < Cr; jj += 4) {
+            float a = __ldg(o.ca_w1 + jj * 64 + lane) * ca_s[c][lane] + __ldg(o.ca_w1 + jj * 64 + lane + 32) * ca_s[c][lane + 32];
+            a = warp_sum(a);
+            if (lane == 0) ca_z[c][jj] = fmaxf(a + __ldg(o.ca_b1 + jj), 0.f);
           }
           ptx::named_bar_sync(bar_id, 128);
           if (row < 64) {
-            float u = b2v;
-            for (int jj = 0; jj < Cr; ++jj) u += (jj < 4 ? w2r[jj] : __ldg(o.ca_w2 + row * Cr + jj)) * ca_z[c][jj];
-            const float yv = 1.f / (1.f + expf(-u));
-            ca_y[c][row] = yv;
-            ca_ds[c][row] = 0.f;
-            if (r == 0) {
-              o.ca_s[(int64_t)n * 64 + row] = ca_s[c][row];
-              o.ca_y[(int64_t)n * 64 + row] = yv;
-            }
+            float u = __ldg(o.ca_b2 + row);
+            for (int jj = 0; jj < Cr; ++jj) u += __ldg(o.ca_w2 + row * Cr + jj) * ca_z[c][jj];
+            o.ca_s[(int64_t)n * 64 + row] = ca_s[c][row];
+            o.ca_y[(int64_t)n * 64 + row] = 1.f / (1.f + expf(-u));
           }
-          ptx::named_bar_sync(bar_id, 128);
         };
-        // backward: ca_y[c][ch] = saved gate, ca_ds[c][ch] = dL/d(mean) / HW from pool_in = sum over pixels of
-        // g * t; the gate's parameter gradients are accumulated once per sample
-        auto gate_bwd = [&](const int* cnt_pool) {
-          float sv = 0.f, b2v = 0.f;
+        // backward: ca_scratch[n][ch] (sum over pixels of g * t) is replaced by dL/d(mean) / HW; the gate's
+        // parameter gradients are accumulated (once per sample: only the completing tile gets here)
+        auto gate_bwd = [&]() {
+          float b2v = 0.f;
           if (row < 64) {
             b2v = __ldg(o.ca_b2 + row);
-            sv = __ldg(o.ca_s + (int64_t)n * 64 + row);
-            ca_s[c][row] = sv;
-            ca_y[c][row] = __ldg(o.ca_y + (int64_t)n * 64 + row);
+            ca_s[c][row] = __ldg(o.ca_s + (int64_t)n * 64 + row);
           }
           ptx::named_bar_sync(bar_id, 128);
           for (int jj = q; jj < Cr; jj += 4) {
@@ -607,19 +583,12 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
             }
           }
           ptx::named_bar_sync(bar_id, 128);
-          float spsn = 0.f;
           if (row < 64) {
             float u = b2v;
             for (int jj = 0; jj < Cr; ++jj) u += __ldg(o.ca_w2 + row * Cr + jj) * ca_z[c][jj];
             const float sp = 1.f / (1.f + expf(-u)), sn = 1.f / (1.f + expf(u));
-            spsn = sp * sn;
+            ca_du[c][row] = __ldcg(o.ca_scratch + (int64_t)n * 64 + row) * (sp * sn);   // sigmoid'(u) from u itself
           }
-          if (store_thread) {
-            wait_counter(cnt_pool, p.tiles_per_sample);
-            CH_TRACE(c, op, TR_POOL);
-          }
-          ptx::named_bar_sync(bar_id, 128);
-          if (row < 64) ca_du[c][row] = __ldcg(o.pool_in + (int64_t)n * 64 + row) * spsn;
           ptx::named_bar_sync(bar_id, 128);
           for (int jj = q; jj < Cr; jj += 4) {
             float dz = __ldg(o.ca_w2 + lane * Cr + jj) * ca_du[c][lane] + __ldg(o.ca_w2 + (lane + 32) * Cr + jj) * ca_du[c][lane + 32];
@@ -630,17 +599,14 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
           if (row < 64) {
             float d = 0.f;
             for (int jj = 0; jj < Cr; ++jj) d += __ldg(o.ca_w1 + jj * 64 + row) * ca_dv[c][jj];
-            ca_ds[c][row] = d * inv_hw;
+            o.ca_scratch[(int64_t)n * 64 + row] = d * inv_hw;
           }
-          if (r == 0) {                              // parameter gradients, once per sample
-            for (int i = row; i < 64 * Cr; i += 128) {
-              atomicAdd(o.ca_dw2 + i, ca_du[c][i / Cr] * ca_z[c][i % Cr]);    // w2 [64][Cr]
-              atomicAdd(o.ca_dw1 + i, ca_dv[c][i / 64] * ca_s[c][i % 64]);    // w1 [Cr][64]
-            }
-            if (row < 64) atomicAdd(o.ca_db2 + row, ca_du[c][row]);
-            if (row < Cr) atomicAdd(o.ca_db1 + row, ca_dv[c][row]);
+          for (int i = row; i < 64 * Cr; i += 128) {
+            atomicAdd(o.ca_dw2 + i, ca_du[c][i / Cr] * ca_z[c][i % Cr]);    // w2 [64][Cr]
+            atomicAdd(o.ca_dw1 + i, ca_dv[c][i / 64] * ca_s[c][i % 64]);    // w1 [Cr][64]
           }
-          ptx::named_bar_sync(bar_id, 128);
+          if (row < 64) atomicAdd(o.ca_db2 + row, ca_du[c][row]);
+          if (row < Cr) atomicAdd(o.ca_db1 + row, ca_dv[c][row]);
         };
         // The conv's input window [18][10] pixels, rewritten in place before the MMAs read it:
         //   v = v * ca_y[ch] + (second window, forward | ca_ds[ch] inside the image, backward);
@@ -648,7 +614,9 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
         // they are stored as a tensor of their own (the RCAB output / dt).  Thread = window row; 16-byte chunks
         // are XOR-swizzled by (row & 7) in both buffers (1024-byte aligned bases).
         auto rewrite_window = [&](const bool second_window) {
-          for (int wr = row; wr < kRows * kP; wr += 128) {
+          // unit = half a window row (four 16-byte chunks): 360 units over 128 threads, at most three each
+          for (int u = row; u < 2 * kRows * kP; u += 128) {
+            const int wr = u >> 1, g0 = (u & 1) * 4;
             const int wh = wr / kP, ww = wr - wh * kP;
             const bool centre = wh >= 1 && wh <= kTH && ww >= 1 && ww <= kTW;
             const int tr = (wh - 1) * kTW + (ww - 1);
@@ -657,8 +625,9 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
             const uint32_t wrow = win + (uint32_t)wr * 128u, xrow = ebuf + (uint32_t)wr * 128u;
             const uint32_t srow = stg + (uint32_t)tr * 128u;
             const uint32_t swr = (uint32_t)(wr & 7), swt = (uint32_t)(tr & 7);
-#pragma unroll 2
-            for (int g = 0; g < 8; ++g) {
+#pragma unroll
+            for (int gg = 0; gg < 4; ++gg) {
+              const int g = g0 + gg;
               const uint32_t off = ((uint32_t)g ^ swr) << 4;
               const uint4 tv = ptx::lds128(wrow + off);
               uint4 xv = make_uint4(0u, 0u, 0u, 0u);
@@ -686,9 +655,17 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
           const bool has_e = o.e != SRB_CHAIN_NONE;
           const bool gate_f = (flags & SRB_CHAIN_GATE_IN) != 0, gate_b = (flags & SRB_CHAIN_GATE_BWD_IN) != 0;
           if (gate_f || gate_b) {
-            const int* cnt_pool = p.counters + ((size_t)(op - 1) * 2 + 1) * N + n;
-            if (gate_f) gate_fwd(cnt_pool);
-            else gate_bwd(cnt_pool);
+            // the gate of this sample: published by the tile of op-1 that completed the sample's sums
+            if (store_thread) {
+              wait_counter(p.counters + ((size_t)(op - 1) * 2 + 1) * N + n, p.tiles_per_sample + 1);
+              CH_TRACE(c, op, TR_POOL);
+            }
+            ptx::named_bar_sync(bar_id, 128);
+            if (row < 64) {
+              ca_y[c][row] = __ldcg(o.ca_y + (int64_t)n * 64 + row);
+              ca_ds[c][row] = gate_b ? __ldcg(o.pool_in + (int64_t)n * 64 + row) : 0.f;
+            }
+            ptx::named_bar_sync(bar_id, 128);
             ptx::mbar_wait(&a_full[c], a_k & 1u);
             if (gate_f) ptx::mbar_wait(&e_full[c], e_k & 1u);
             rewrite_window(gate_f);
@@ -818,11 +795,8 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
             }
             if (flags & SRB_COLSUM)
               late_colsum(stg, o.colsum + (int64_t)(o.colsum_groups > 1 ? n : 0) * 64, o.colsum_scale);
-            if (flags & SRB_CHAIN_POOL_OUT) {
-              // the sums above are this sample's CALayer pool: publish them; the NEXT op's tiles wait for them
-              ptx::named_bar_sync(bar_id, 128);
-              if (store_thread) red_release_gpu(cnt_part, 1);
-            }
+            // POOL_OUT: the sums above are this sample's CALayer pool; they are counted in with the publish below
+            if (flags & SRB_CHAIN_POOL_OUT) ptx::named_bar_sync(bar_id, 128);
             if (flags & SRB_CHAIN_PROD_OUT) {
               // y (just staged) is dL/dout of an RCAB, tile e2 its saved pre-attention tensor t: per-sample sums
               // of g*t for the gate's backward, published the same way
@@ -834,7 +808,6 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
                 atomicAdd(o.ca_scratch + (int64_t)n * 64 + row, tot);
               }
               ptx::named_bar_sync(bar_id, 128);
-              if (store_thread) red_release_gpu(cnt_part, 1);
               ++e2_k;
             }
             if (flags & SRB_CHAIN_CA_BWD_FUSED) {
@@ -956,7 +929,12 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
         }
         ++a_k;
         // ---- publish: outputs complete in global memory, then release the sample counter ----
+        const bool sums_out = o.kind == SRB_CHAIN_CONV && (flags & (SRB_CHAIN_POOL_OUT | SRB_CHAIN_PROD_OUT)) != 0;
         if (store_thread) {
+          // POOL_OUT / PROD_OUT: count this tile's contribution to the sample's sums in (it is complete: barrier
+          // above); the tile that finds every other tile already counted evaluates the gate below.  The atomic's
+          // round trip runs under the TMA store that is still in flight.
+          if (sums_out) last_s[c] = atom_add_acq_rel_gpu(cnt_part, 1) == p.tiles_per_sample - 1;
           ptx::bulk_wait_group<0>();
           if (o.kind == SRB_CHAIN_CONV && (flags & SRB_CHAIN_CA)) ptx::mbar_arrive(&e_empty[c]);   // out was staged in it
           if (o.kind == SRB_CHAIN_CONV && (flags & (SRB_CHAIN_CA_BWD_FUSED | SRB_CHAIN_PROD_OUT))) ptx::mbar_arrive(&e2_empty[c]);   // so was dt
@@ -966,6 +944,14 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
           CH_TRACE(c, op, TR_RELEASED);
         }
         ptx::named_bar_sync(bar_id, 128);          // staging buffer free before the next item writes it
+        if (sums_out && last_s[c]) {
+          // every tile of sample n has added its sums (acquired by the counter increment above, made visible to
+          // the warpgroup by the barrier): evaluate the gate once, then raise the counter to tiles + 1
+          if (flags & SRB_CHAIN_POOL_OUT) gate_fwd();
+          else gate_bwd();
+          ptx::named_bar_sync(bar_id, 128);
+          if (store_thread) red_release_gpu(cnt_part, 1);
+        }
       }
     }
   }
@@ -1087,12 +1073,18 @@ extern "C" int srb_conv_chain(srb_ctx* ctx, const srb_chain_desc* d, void* strea
                   "srb_conv_chain: op %d: COLSUM needs a pointer and groups in {1, N}", i);
       SRB_REQUIRE((o.e2 != SRB_CHAIN_NONE) == ((o.flags & (SRB_CHAIN_CA_BWD_FUSED | SRB_CHAIN_PROD_OUT)) != 0),
                   "srb_conv_chain: op %d: a second operand tile goes with CA_BWD_FUSED / PROD_OUT and only with them", i);
-      if (o.flags & SRB_CHAIN_POOL_OUT)
+      if (o.flags & SRB_CHAIN_POOL_OUT) {
         SRB_REQUIRE((o.flags & SRB_COLSUM) && o.colsum_groups == d->N && !(o.flags & (SRB_CHAIN_CA | SRB_CHAIN_CA_BWD_FUSED)),
                     "srb_conv_chain: op %d: POOL_OUT needs COLSUM per sample and excludes the fused CA forms", i);
+        SRB_REQUIRE(o.ca_w1 && o.ca_b1 && o.ca_w2 && o.ca_b2 && o.ca_s && o.ca_y && o.ca_cr >= 1 && o.ca_cr <= kMaxCr,
+                    "srb_conv_chain: op %d: POOL_OUT gate parameters missing or Cr outside [1,%d]", i, kMaxCr);
+      }
       if (o.flags & SRB_CHAIN_PROD_OUT) {
         SRB_REQUIRE(!(o.flags & (SRB_COLSUM | SRB_CHAIN_CA | SRB_CHAIN_CA_BWD_FUSED | SRB_CHAIN_POOL_OUT)) && o.ca_scratch,
                     "srb_conv_chain: op %d: PROD_OUT needs ca_scratch and excludes COLSUM / CA / POOL_OUT", i);
+        SRB_REQUIRE(o.ca_w1 && o.ca_b1 && o.ca_w2 && o.ca_b2 && o.ca_s && o.ca_y && o.ca_dw1 && o.ca_db1 && o.ca_dw2 &&
+                        o.ca_db2 && o.ca_cr >= 1 && o.ca_cr <= kMaxCr,
+                    "srb_conv_chain: op %d: PROD_OUT gate pointers missing or Cr outside [1,%d]", i, kMaxCr);
         if ((rc = check_ref(o.e2, true, "saved t", i))) return rc;
       }
       if (o.flags & (SRB_CHAIN_GATE_IN | SRB_CHAIN_GATE_BWD_IN)) {
@@ -1101,18 +1093,14 @@ extern "C" int srb_conv_chain(srb_ctx* ctx, const srb_chain_desc* d, void* strea
         SRB_REQUIRE(i > 0 && d->ops[i - 1].kind == SRB_CHAIN_CONV &&
                         (d->ops[i - 1].flags & (f ? SRB_CHAIN_POOL_OUT : SRB_CHAIN_PROD_OUT)),
                     "srb_conv_chain: op %d: a gated input needs op %d to publish its sums (POOL_OUT / PROD_OUT)", i, i - 1);
-        SRB_REQUIRE(o.pool_in == (f ? d->ops[i - 1].colsum : d->ops[i - 1].ca_scratch),
-                    "srb_conv_chain: op %d: pool_in must be the buffer op %d publishes", i, i - 1);
+        SRB_REQUIRE(o.ca_y && o.ca_y == d->ops[i - 1].ca_y && (f || o.pool_in == d->ops[i - 1].ca_scratch),
+                    "srb_conv_chain: op %d: ca_y (and pool_in, backward) must be the buffers op %d publishes", i, i - 1);
         SRB_REQUIRE(!(o.flags & (SRB_CHAIN_CA | SRB_CHAIN_CA_BWD_FUSED)), "srb_conv_chain: op %d: gated input excludes the fused CA forms", i);
-        SRB_REQUIRE(o.ca_w1 && o.ca_b1 && o.ca_w2 && o.ca_b2 && o.ca_s && o.ca_y && o.ca_cr >= 1 && o.ca_cr <= kMaxCr,
-                    "srb_conv_chain: op %d: gate parameters missing or Cr outside [1,%d]", i, kMaxCr);
         if ((rc = check_ref(o.y2, true, "gated tile output", i))) return rc;
         if (f) {
           if ((rc = check_ref(o.xs, true, "skip window", i))) return rc;
           SRB_REQUIRE(o.e2 == SRB_CHAIN_NONE, "srb_conv_chain: op %d: GATE_IN's second window occupies the e2 tile", i);
           any_gate_in = true;
-        } else {
-          SRB_REQUIRE(o.ca_dw1 && o.ca_db1 && o.ca_dw2 && o.ca_db2, "srb_conv_chain: op %d: GATE_BWD_IN gradient pointers missing", i);
         }
       }
       if (o.e2 != SRB_CHAIN_NONE) any_e2 = true;

@@ -277,9 +277,10 @@ class RCANGroupFn(Function):
                 else:
                     ch.conv(ref(0, 3 * b - 2), ref(0, 3 * b), 2 * b, b1, relu=True, gate_in=pending)
                     cur = ref(0, 3 * b - 1)
-                ch.conv(ref(0, 3 * b), ref(0, 3 * b + 1), 2 * b + 1, b2, colsum=pool[b], colsum_groups=n, pool_out=True)
-                pending = dict(skip=cur, out=ref(0, 3 * b + 2), pool=pool[b], w1=cw1.reshape(cw1.shape[0], 64), b1=cb1,
-                               w2=cw2.reshape(64, cw2.shape[1]), b2=cb2, s=s_all[b], y=y_all[b])
+                ch.conv(ref(0, 3 * b), ref(0, 3 * b + 1), 2 * b + 1, b2, colsum=pool[b], colsum_groups=n,
+                        pool_out=dict(w1=cw1.reshape(cw1.shape[0], 64), b1=cb1, w2=cw2.reshape(64, cw2.shape[1]), b2=cb2,
+                                      s=s_all[b], y=y_all[b]))
+                pending = dict(skip=cur, out=ref(0, 3 * b + 2), y=y_all[b])
             ch.conv(ref(0, 3 * nb - 2), ref(0, 3 * nb), 2 * nb, params[-1].detach(), res=xin, gate_in=pending)
         else:
             for b in range(nb):
@@ -325,15 +326,23 @@ class RCANGroupFn(Function):
                         db1=dcb1, dw2=dcw2.view(64, cr), db2=dcb2, scratch=scratch[b], colsum_dt=db2)
 
         deferred = gate_deferred()
+        ca_cache = {}
+
+        def ca_once(b):
+            if b not in ca_cache:
+                ca_cache[b] = ca_args(b)      # claims the gradient targets of RCAB b: exactly once
+            return ca_cache[b]
 
         def gate_args(b):
             """Deferred CALayer backward of RCAB b, applied to the input window of conv2's dgrad."""
-            a = ca_args(b)
-            return dict(dt=a["dt"], pool=a["scratch"], w1=a["w1"], b1=a["b1"], w2=a["w2"], b2=a["b2"], s=a["s"], y=a["y"],
-                        dw1=a["dw1"], db1=a["db1"], dw2=a["dw2"], db2=a["db2"], colsum_dt=a["colsum_dt"])
+            a = ca_once(b)
+            return dict(dt=a["dt"], ds=a["scratch"], y=a["y"], colsum_dt=a["colsum_dt"])
 
         def prod_args(b):
-            return dict(t=ref(1, 3 * b + 1), scratch=scratch[b])
+            """dgrad op that produces dL/dout of RCAB b: publishes sum(g*t), the completing tile runs the gate backward."""
+            a = ca_once(b)
+            return dict(t=a["t"], scratch=a["scratch"], w1=a["w1"], b1=a["b1"], w2=a["w2"], b2=a["b2"], s=a["s"], y=a["y"],
+                        dw1=a["dw1"], db1=a["db1"], dw2=a["dw2"], db2=a["db2"])
 
         # group tail conv: out = conv(last) + x; its input gradient is dL/dout of the last RCAB
         if deferred:

@@ -514,37 +514,41 @@ class Chain:
         return t.data_ptr()
 
     def conv(self, x, y, w_layer, bias=None, *, relu=False, scale=1.0, res=None, mask=None, colsum=None, colsum_groups=1,
-             colsum_scale=1.0, ca_bwd=None, pool_out=False, prod_out=None, gate_in=None, gate_bwd_in=None):
+             colsum_scale=1.0, ca_bwd=None, pool_out=None, prod_out=None, gate_in=None, gate_bwd_in=None):
         """ca_bwd: dict(t=ref, dt=ref, w1, b1, w2, b2, s, y, dw1, db1, dw2, db2, scratch, colsum_dt) — fuse the
         CALayer backward of the block whose dL/dout this conv produces (SRB_CHAIN_CA_BWD_FUSED).
 
-        Deferred-gate forms (include/srb200.h): pool_out=True publishes `colsum` [N][64] as a CALayer pool;
-        gate_in=dict(skip=ref, out=ref, pool, w1, b1, w2, b2, s, y): the input is x*gate + skip (both read as
-        windows), its tile is also stored to `out`; prod_out=dict(t=ref, scratch): publishes the per-sample
-        sums of y*t; gate_bwd_in=dict(dt=ref, pool, w1, b1, w2, b2, s, y, dw1, db1, dw2, db2, colsum_dt): the
-        input is x*gate + ds/HW (the CALayer backward), its tile is stored to `dt`."""
+        Deferred-gate forms (include/srb200.h).  The tile that completes a sample's sums evaluates the gate
+        once for the sample; the next conv applies it to its own input window.
+          pool_out=dict(w1, b1, w2, b2, s, y): `colsum` [N][64] is a CALayer pool; gate -> y, mean -> s.
+          gate_in=dict(skip=ref, out=ref, y): the input is x*y + skip (both read as windows); its tile is
+            also stored to `out`.
+          prod_out=dict(t=ref, scratch, w1, b1, w2, b2, s, y, dw1, db1, dw2, db2): per-sample sums of
+            (this op's output)*t -> scratch, replaced by dL/d(mean)/HW; gate parameter gradients accumulated.
+          gate_bwd_in=dict(dt=ref, ds, y, colsum_dt): the input is x*y + ds inside the image (ds = the
+            `scratch` of the op before); its tile is stored to `dt`, its column sums added to colsum_dt."""
         o = self._op(L.CHAIN_CONV, x, y)
         if ca_bwd is not None:
             self._fill_ca_bwd(o, **ca_bwd)
+        if pool_out is not None and pool_out is not False:
+            po = pool_out
+            o.ca_cr = po["w1"].shape[0]
+            o.ca_w1, o.ca_b1, o.ca_w2, o.ca_b2 = (self._ptr(po[k]) for k in ("w1", "b1", "w2", "b2"))
+            o.ca_s, o.ca_y = self._ptr(po["s"]), self._ptr(po["y"])
         if gate_in is not None:
-            gi = gate_in
-            o.xs, o.y2 = gi["skip"], gi["out"]
-            o.ca_cr = gi["w1"].shape[0]
-            o.ca_w1, o.ca_b1, o.ca_w2, o.ca_b2 = (self._ptr(gi[k]) for k in ("w1", "b1", "w2", "b2"))
-            o.ca_s, o.ca_y = self._ptr(gi["s"]), self._ptr(gi["y"])
-            o.pool_in = self._ptr(gi["pool"])
+            o.xs, o.y2 = gate_in["skip"], gate_in["out"]
+            o.ca_y = self._ptr(gate_in["y"])
+        if prod_out is not None:
+            po = prod_out
+            o.e2 = po["t"]
+            self._fill_ca_params(o, po["w1"], po["b1"], po["w2"], po["b2"], po["s"], po["y"], po["dw1"], po["db1"],
+                                 po["dw2"], po["db2"], po["scratch"])
         if gate_bwd_in is not None:
             gb = gate_bwd_in
             o.y2 = gb["dt"]
-            o.ca_cr = gb["w1"].shape[0]
-            o.ca_w1, o.ca_b1, o.ca_w2, o.ca_b2 = (self._ptr(gb[k]) for k in ("w1", "b1", "w2", "b2"))
-            o.ca_s, o.ca_y = self._ptr(gb["s"]), self._ptr(gb["y"])
-            o.ca_dw1, o.ca_db1, o.ca_dw2, o.ca_db2 = (self._ptr(gb[k]) for k in ("dw1", "db1", "dw2", "db2"))
+            o.ca_y = self._ptr(gb["y"])
+            o.pool_in = self._ptr(gb["ds"])
             o.colsum2 = self._ptr(gb.get("colsum_dt"))
-            o.pool_in = self._ptr(gb["pool"])
-        if prod_out is not None:
-            o.e2 = prod_out["t"]
-            o.ca_scratch = self._ptr(prod_out["scratch"])
         o.w_layer, o.scale = w_layer, float(scale)
         o.flags = (L.RELU if relu else 0) | (L.RESIDUAL if res is not None else 0) | (L.MASK if mask is not None else 0) | \
                   (L.COLSUM if colsum is not None else 0)
@@ -554,7 +558,7 @@ class Chain:
             o.e = mask
         if ca_bwd is not None:
             o.flags |= L.CHAIN_CA_BWD_FUSED
-        if pool_out:
+        if pool_out is not None and pool_out is not False:
             o.flags |= L.CHAIN_POOL_OUT
         if prod_out is not None:
             o.flags |= L.CHAIN_PROD_OUT
