@@ -165,24 +165,8 @@ int  srb_wgrad_uses_umma(const srb_wgrad_desc*);
  * counters: n_ops * 2 * N int32, zero on entry. */
 enum { SRB_CHAIN_CONV = 0, SRB_CHAIN_CA_BWD = 1 };
 enum { SRB_CHAIN_CA = 32,              /* extra flag bits for SRB_CHAIN_CONV ops */
-       SRB_CHAIN_CA_BWD_FUSED = 64,    /* after y is stored, run CA_BWD on it: g = y, t = tile e2, dt -> y2,
+       SRB_CHAIN_CA_BWD_FUSED = 64 };  /* after y is stored, run CA_BWD on it: g = y, t = tile e2, dt -> y2,
                                           column sums of dt -> colsum2 (saves a whole dependent op per RCAB) */
-       /* "Deferred gate" forms: the sample-wide reduction of a CALayer no longer stalls the op that produces
-        * its operand; the NEXT conv applies the gate to its own input window while that window is in shared
-        * memory, so the reduction's round trip overlaps the halo exchange instead of preceding it.
-        *   POOL_OUT: after y is stored, add y's per-sample column sums to colsum [N][64] (COLSUM, groups N)
-        *     and publish them (the op's second counter); the op itself waits for nothing.
-        *   GATE_IN (forward, rcan.py:23-29,54): the conv's input is x*gate + xs, gate = sigmoid(W2 relu(W1
-        *     mean + b1) + b2) from pool_in [N][64] (= colsum of op i-1, which must be POOL_OUT); x and xs are
-        *     read as windows; the tile's own 128 pixels of that input are also stored to y2 (the RCAB output),
-        *     mean / gate to ca_s / ca_y.  A RESIDUAL tile `e` may be combined with it.
-        *   PROD_OUT: after y is stored, add the per-sample column sums of y (*) tile e2 to ca_scratch [N][64]
-        *     and publish them (backward: sum over pixels of dL/dout * t).
-        *   GATE_BWD_IN (backward of the above): the conv's input is dt = x*ca_y + ds/HW inside the image,
-        *     ds from the gate's backward with pool_in [N][64] (= ca_scratch of op i-1, which must be
-        *     PROD_OUT); dt's tile is stored to y2, its column sums to colsum2, the gate's parameter
-        *     gradients are accumulated into ca_dw1..ca_db2. */
-       SRB_CHAIN_POOL_OUT = 128, SRB_CHAIN_PROD_OUT = 256, SRB_CHAIN_GATE_IN = 512, SRB_CHAIN_GATE_BWD_IN = 1024 };
 #define SRB_CHAIN_NONE 0xFFFFu
 #define SRB_CHAIN_MAX_OPS 64
 
@@ -190,7 +174,7 @@ typedef struct srb_chain_op {
   int32_t  kind;
   uint32_t flags;
   uint16_t x, y, e, y2;     /* buffer references */
-  uint16_t e2, xs;          /* e2: second operand tile (CA_BWD_FUSED / PROD_OUT: the saved t); xs: GATE_IN's skip window */
+  uint16_t e2, reserved0;   /* second operand tile (SRB_CHAIN_CA_BWD_FUSED: the saved t) */
   int32_t  w_layer;         /* index into the packed filter bank (CONV) */
   float    scale;
   int32_t  colsum_groups;   /* 1 -> colsum[64]; N -> colsum[N][64] (always N with SRB_CHAIN_CA) */
@@ -202,8 +186,7 @@ typedef struct srb_chain_op {
   const float *ca_w1, *ca_b1, *ca_w2, *ca_b2;   /* conv_du.0 [Cr][64], [Cr]; conv_du.2 [64][Cr], [64] */
   float   *ca_s, *ca_y;                         /* [N][64]: written by SRB_CHAIN_CA, read by CA_BWD */
   float   *ca_dw1, *ca_db1, *ca_dw2, *ca_db2;   /* CA_BWD: accumulated */
-  float   *ca_scratch;                          /* CA_BWD / PROD_OUT: [N][64] zero-filled */
-  const float* pool_in;                         /* GATE_IN / GATE_BWD_IN: [N][64] sums published by op i-1 */
+  float   *ca_scratch;                          /* CA_BWD: [N][64] zero-filled */
 } srb_chain_op;
 
 typedef struct srb_chain_desc {

@@ -62,11 +62,6 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ int atom_add_acq_rel_gpu(int* p, int v) {
-  int old;
-  asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
-  return old;
-}
 __device__ __forceinline__ void red_release_gpu(int* p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -204,9 +199,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t w_full[3], w_empty[3];
   __shared__ uint64_t a_full[2], a_empty[2], e_full[2], e_empty[2], e2_full[2], e2_empty[2], acc_full[2], acc_empty[2];
-  __shared__ uint64_t g_full[2];   // deferred-gate ops: the epilogue warpgroup has rewritten the window in place
   __shared__ uint32_t tmem_slot;
-  __shared__ int last_s[2];        // POOL_OUT / PROD_OUT: this tile completed its sample's sums
   __shared__ __align__(16) float bias_s[2][64];
   __shared__ float colsum_s[2][4][64];
   __shared__ float ca_s[2][64], ca_y[2][64], ca_du[2][64], ca_ds[2][64], ca_z[2][kMaxCr], ca_dv[2][kMaxCr];
@@ -233,7 +226,6 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
       ptx::mbar_init(&e2_empty[c], 1);
       ptx::mbar_init(&acc_full[c], 1);
       ptx::mbar_init(&acc_empty[c], 1);
-      ptx::mbar_init(&g_full[c], 1);
     }
     ptx::fence_mbar_init();
   }
@@ -281,14 +273,6 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
             tma_load_5d(win, &maps.tile[ref_space(o.x)], &a_full[c], 0, w0, h0, n, ref_slot(o.x));
           }
           ++a_k;
-          if (o.flags & SRB_CHAIN_GATE_IN) {
-            // second window (the RCAB's skip input) into the operand-tile area [ebuf, ebuf + 22.5 KB): one
-            // more use of the e buffer, so a RESIDUAL tile of the same op follows once it has been consumed
-            ptx::mbar_wait(&e_empty[c], (e_k & 1u) ^ 1u);
-            ptx::mbar_arrive_expect_tx(&e_full[c], kWinBytes);
-            tma_load_5d(ebuf, &maps.win[ref_space(o.xs)], &e_full[c], 0, w0 - 1, h0 - 1, n, ref_slot(o.xs));
-            ++e_k;
-          }
           if (o.e != SRB_CHAIN_NONE) {
             ptx::mbar_wait(&e_empty[c], (e_k & 1u) ^ 1u);
             ptx::mbar_arrive_expect_tx(&e_full[c], kTileBytes);
@@ -310,7 +294,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
       const uint32_t w_lo = ptx::smem_desc_lo(wbase, 16u);
       const uint32_t a_lo0 = ptx::smem_desc_lo(base + kWBytes, 16u);
       const uint32_t a_lo1 = ptx::smem_desc_lo(base + kWBytes + kChainStride, 16u);
-      uint32_t a_k0 = 0, a_k1 = 0, acc_k0 = 0, acc_k1 = 0, w_k = 0, g_k0 = 0, g_k1 = 0;
+      uint32_t a_k0 = 0, a_k1 = 0, acc_k0 = 0, acc_k1 = 0, w_k = 0;
       for (int op = 0; op < p.n_ops; ++op) {
         const srb_chain_op& o = p.ops[op];
         if (o.kind != SRB_CHAIN_CONV) {
@@ -327,16 +311,11 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
           }
           continue;
         }
-        const bool gated = (o.flags & (SRB_CHAIN_GATE_IN | SRB_CHAIN_GATE_BWD_IN)) != 0;
         // the two chains are written out separately so that every descriptor is a loop-invariant
         // (uniform-register) base plus an immediate: the issuing thread has ~48 cycles per MMA
         for (int j = 0; j < my_tiles; j += 2) {
           ptx::mbar_wait(&acc_empty[0], (acc_k0 & 1u) ^ 1u);
           ptx::mbar_wait(&a_full[0], a_k0 & 1u);
-          if (gated) {
-            ptx::mbar_wait(&g_full[0], g_k0 & 1u);
-            ++g_k0;
-          }
           ptx::tc_fence_after();
           CH_TRACE(0, op, TR_AFULL);
           mma_tile(tmem_acc, a_lo0, w_lo, w_full, w_empty, j == 0, j == my_tiles - 1, w_k & 1u);
@@ -348,10 +327,6 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
           if (j + 1 < my_tiles) {
             ptx::mbar_wait(&acc_empty[1], (acc_k1 & 1u) ^ 1u);
             ptx::mbar_wait(&a_full[1], a_k1 & 1u);
-            if (gated) {
-              ptx::mbar_wait(&g_full[1], g_k1 & 1u);
-              ++g_k1;
-            }
             ptx::tc_fence_after();
             CH_TRACE(1, op, TR_AFULL);
             mma_tile(tmem_acc + 64u, a_lo1, w_lo, w_full, w_empty, false, j + 1 == my_tiles - 1, w_k & 1u);
@@ -545,144 +520,8 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
           }
         };
 
-        // ---- deferred gate: the tile that completes a sample's sums (POOL_OUT / PROD_OUT) evaluates the gate ONCE
-        // for the sample and publishes it; the tiles of the next op (GATE_IN / GATE_BWD_IN) only read 64 values ----
-        // forward: ca_y[n][ch] = sigmoid(W2 relu(W1 mean + b1) + b2) (rcan.py:17-28); mean / gate saved for backward
-        auto gate_fwd = [&]() {
-          if (row < 64) ca_s[c][row] = __ldcg(o.colsum + (int64_t)n * 64 + row) * inv_hw;
-          ptx::named_bar_sync(bar_id, 128);
-          for (int jj = q; jj < Cr; jj += 4) {
-            float a = __ldg(o.ca_w1 + jj * 64 + lane) * ca_s[c][lane] + __ldg(o.ca_w1 + jj * 64 + lane + 32) * ca_s[c][lane + 32];
-            a = warp_sum(a);
-            if (lane == 0) ca_z[c][jj] = fmaxf(a + __ldg(o.ca_b1 + jj), 0.f);
-          }
-          ptx::named_bar_sync(bar_id, 128);
-          if (row < 64) {
-            float u = __ldg(o.ca_b2 + row);
-            for (int jj = 0; jj < Cr; ++jj) u += __ldg(o.ca_w2 + row * Cr + jj) * ca_z[c][jj];
-            o.ca_s[(int64_t)n * 64 + row] = ca_s[c][row];
-            o.ca_y[(int64_t)n * 64 + row] = 1.f / (1.f + expf(-u));
-          }
-        };
-        // backward: ca_scratch[n][ch] (sum over pixels of g * t) is replaced by dL/d(mean) / HW; the gate's
-        // parameter gradients are accumulated (once per sample: only the completing tile gets here)
-        auto gate_bwd = [&]() {
-          float b2v = 0.f;
-          if (row < 64) {
-            b2v = __ldg(o.ca_b2 + row);
-            ca_s[c][row] = __ldg(o.ca_s + (int64_t)n * 64 + row);
-          }
-          ptx::named_bar_sync(bar_id, 128);
-          for (int jj = q; jj < Cr; jj += 4) {
-            float a = __ldg(o.ca_w1 + jj * 64 + lane) * ca_s[c][lane] + __ldg(o.ca_w1 + jj * 64 + lane + 32) * ca_s[c][lane + 32];
-            a = warp_sum(a);
-            if (lane == 0) {
-              a += __ldg(o.ca_b1 + jj);
-              ca_z[c][jj] = fmaxf(a, 0.f);
-              ca_dv[c][jj] = a > 0.f ? 1.f : 0.f;
-            }
-          }
-          ptx::named_bar_sync(bar_id, 128);
-          if (row < 64) {
-            float u = b2v;
-            for (int jj = 0; jj < Cr; ++jj) u += __ldg(o.ca_w2 + row * Cr + jj) * ca_z[c][jj];
-            const float sp = 1.f / (1.f + expf(-u)), sn = 1.f / (1.f + expf(u));
-            ca_du[c][row] = __ldcg(o.ca_scratch + (int64_t)n * 64 + row) * (sp * sn);   // sigmoid'(u) from u itself
-          }
-          ptx::named_bar_sync(bar_id, 128);
-          for (int jj = q; jj < Cr; jj += 4) {
-            float dz = __ldg(o.ca_w2 + lane * Cr + jj) * ca_du[c][lane] + __ldg(o.ca_w2 + (lane + 32) * Cr + jj) * ca_du[c][lane + 32];
-            dz = warp_sum(dz);
-            if (lane == 0) ca_dv[c][jj] *= dz;
-          }
-          ptx::named_bar_sync(bar_id, 128);
-          if (row < 64) {
-            float d = 0.f;
-            for (int jj = 0; jj < Cr; ++jj) d += __ldg(o.ca_w1 + jj * 64 + row) * ca_dv[c][jj];
-            o.ca_scratch[(int64_t)n * 64 + row] = d * inv_hw;
-          }
-          for (int i = row; i < 64 * Cr; i += 128) {
-            atomicAdd(o.ca_dw2 + i, ca_du[c][i / Cr] * ca_z[c][i % Cr]);    // w2 [64][Cr]
-            atomicAdd(o.ca_dw1 + i, ca_dv[c][i / 64] * ca_s[c][i % 64]);    // w1 [Cr][64]
-          }
-          if (row < 64) atomicAdd(o.ca_db2 + row, ca_du[c][row]);
-          if (row < Cr) atomicAdd(o.ca_db1 + row, ca_dv[c][row]);
-        };
-        // The conv's input window [18][10] pixels, rewritten in place before the MMAs read it:
-        //   v = v * ca_y[ch] + (second window, forward | ca_ds[ch] inside the image, backward);
-        // the tile's own 128 pixels (window rows 1..16, columns 1..8) are copied to the staging buffer, from where
-        // they are stored as a tensor of their own (the RCAB output / dt).  Thread = window row; 16-byte chunks
-        // are XOR-swizzled by (row & 7) in both buffers (1024-byte aligned bases).
-        auto rewrite_window = [&](const bool second_window) {
-          // unit = half a window row (four 16-byte chunks): 360 units over 128 threads, at most three each
-          for (int u = row; u < 2 * kRows * kP; u += 128) {
-            const int wr = u >> 1, g0 = (u & 1) * 4;
-            const int wh = wr / kP, ww = wr - wh * kP;
-            const bool centre = wh >= 1 && wh <= kTH && ww >= 1 && ww <= kTW;
-            const int tr = (wh - 1) * kTW + (ww - 1);
-            const int ih = h0 - 1 + wh, iw = w0 - 1 + ww;
-            const bool inside = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
-            const uint32_t wrow = win + (uint32_t)wr * 128u, xrow = ebuf + (uint32_t)wr * 128u;
-            const uint32_t srow = stg + (uint32_t)tr * 128u;
-            const uint32_t swr = (uint32_t)(wr & 7), swt = (uint32_t)(tr & 7);
-#pragma unroll
-            for (int gg = 0; gg < 4; ++gg) {
-              const int g = g0 + gg;
-              const uint32_t off = ((uint32_t)g ^ swr) << 4;
-              const uint4 tv = ptx::lds128(wrow + off);
-              uint4 xv = make_uint4(0u, 0u, 0u, 0u);
-              if (second_window) xv = ptx::lds128(xrow + off);
-              const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w}, xw[4] = {xv.x, xv.y, xv.z, xv.w};
-              uint32_t pk[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 ft = unpack_bf16x2(tw[e]), fx = unpack_bf16x2(xw[e]);
-                const int ch = g * 8 + e * 2;
-                if (second_window)
-                  pk[e] = pack_bf16x2(fmaf(ft.x, ca_y[c][ch], fx.x), fmaf(ft.y, ca_y[c][ch + 1], fx.y));
-                else
-                  pk[e] = inside ? pack_bf16x2(fmaf(ft.x, ca_y[c][ch], ca_ds[c][ch]), fmaf(ft.y, ca_y[c][ch + 1], ca_ds[c][ch + 1]))
-                                 : 0u;
-              }
-              const uint4 ov = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              ptx::sts128(wrow + off, ov);
-              if (centre) ptx::sts128(srow + (((uint32_t)g ^ swt) << 4), ov);
-            }
-          }
-        };
-
         if (o.kind == SRB_CHAIN_CONV) {
           const bool has_e = o.e != SRB_CHAIN_NONE;
-          const bool gate_f = (flags & SRB_CHAIN_GATE_IN) != 0, gate_b = (flags & SRB_CHAIN_GATE_BWD_IN) != 0;
-          if (gate_f || gate_b) {
-            // the gate of this sample: published by the tile of op-1 that completed the sample's sums
-            if (store_thread) {
-              wait_counter(p.counters + ((size_t)(op - 1) * 2 + 1) * N + n, p.tiles_per_sample + 1);
-              CH_TRACE(c, op, TR_POOL);
-            }
-            ptx::named_bar_sync(bar_id, 128);
-            if (row < 64) {
-              ca_y[c][row] = __ldcg(o.ca_y + (int64_t)n * 64 + row);
-              ca_ds[c][row] = gate_b ? __ldcg(o.pool_in + (int64_t)n * 64 + row) : 0.f;
-            }
-            ptx::named_bar_sync(bar_id, 128);
-            ptx::mbar_wait(&a_full[c], a_k & 1u);
-            if (gate_f) ptx::mbar_wait(&e_full[c], e_k & 1u);
-            rewrite_window(gate_f);
-            ptx::fence_proxy_async_smem();
-            ptx::named_bar_sync(bar_id, 128);
-            if (store_thread) {
-              ptx::mbar_arrive(&g_full[c]);                    // the MMA issuer may read the window now
-              if (gate_f) ptx::mbar_arrive(&e_empty[c]);       // second window consumed
-              tma_store_5d(&maps.tile[ref_space(o.y2)], stg, 0, w0, h0, n, ref_slot(o.y2));
-              ptx::bulk_commit_group();
-            }
-            if (gate_f) ++e_k;
-            if (gate_b && o.colsum2) late_colsum(stg, o.colsum2, 0.f);   // bias gradient of the conv that produced t
-            // the staging buffer is rewritten by this op's own epilogue: its store must have read it (the MMAs
-            // take > 1 us, the wait is over long before)
-            if (store_thread) ptx::bulk_wait_group_read<0>();
-          }
           const bool ca = (flags & SRB_CHAIN_CA) != 0;
           // the bias of this op is cold in L1 (every op has its own): fetch it into shared memory
           // while the MMAs run instead of stalling each 32-column chunk on an L2 round trip
@@ -767,7 +606,6 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
               epilogue(std::integral_constant<uint32_t, SRB_RESIDUAL | SRB_COLSUM | SRB_CHAIN_CA>{});
               break;
             case 0: epilogue(std::integral_constant<uint32_t, 0>{}); break;
-            case SRB_COLSUM: epilogue(std::integral_constant<uint32_t, SRB_COLSUM>{}); break;
             default: epilogue(std::integral_constant<uint32_t, kGeneric>{}); break;
           }
           ptx::tc_fence_before();
@@ -795,21 +633,6 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
             }
             if (flags & SRB_COLSUM)
               late_colsum(stg, o.colsum + (int64_t)(o.colsum_groups > 1 ? n : 0) * 64, o.colsum_scale);
-            // POOL_OUT: the sums above are this sample's CALayer pool; they are counted in with the publish below
-            if (flags & SRB_CHAIN_POOL_OUT) ptx::named_bar_sync(bar_id, 128);
-            if (flags & SRB_CHAIN_PROD_OUT) {
-              // y (just staged) is dL/dout of an RCAB, tile e2 its saved pre-attention tensor t: per-sample sums
-              // of g*t for the gate's backward, published the same way
-              ptx::mbar_wait(&e2_full[c], e2_k & 1u);
-              tile_prod_colsum_lds(stg, e2buf, q, lane, colsum_s[c][q]);
-              ptx::named_bar_sync(bar_id, 128);
-              if (row < 64) {
-                const float tot = (colsum_s[c][0][row] + colsum_s[c][1][row]) + (colsum_s[c][2][row] + colsum_s[c][3][row]);
-                atomicAdd(o.ca_scratch + (int64_t)n * 64 + row, tot);
-              }
-              ptx::named_bar_sync(bar_id, 128);
-              ++e2_k;
-            }
             if (flags & SRB_CHAIN_CA_BWD_FUSED) {
               // y (just staged, bf16) is dL/dout of the previous RCAB: run its CALayer backward here
               // instead of as a dependent op.  The staging buffer is only READ (the store of y may
@@ -929,29 +752,16 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
         }
         ++a_k;
         // ---- publish: outputs complete in global memory, then release the sample counter ----
-        const bool sums_out = o.kind == SRB_CHAIN_CONV && (flags & (SRB_CHAIN_POOL_OUT | SRB_CHAIN_PROD_OUT)) != 0;
         if (store_thread) {
-          // POOL_OUT / PROD_OUT: count this tile's contribution to the sample's sums in (it is complete: barrier
-          // above); the tile that finds every other tile already counted evaluates the gate below.  The atomic's
-          // round trip runs under the TMA store that is still in flight.
-          if (sums_out) last_s[c] = atom_add_acq_rel_gpu(cnt_part, 1) == p.tiles_per_sample - 1;
           ptx::bulk_wait_group<0>();
           if (o.kind == SRB_CHAIN_CONV && (flags & SRB_CHAIN_CA)) ptx::mbar_arrive(&e_empty[c]);   // out was staged in it
-          if (o.kind == SRB_CHAIN_CONV && (flags & (SRB_CHAIN_CA_BWD_FUSED | SRB_CHAIN_PROD_OUT))) ptx::mbar_arrive(&e2_empty[c]);   // so was dt
+          if (o.kind == SRB_CHAIN_CONV && (flags & SRB_CHAIN_CA_BWD_FUSED)) ptx::mbar_arrive(&e2_empty[c]);   // so was dt
           CH_TRACE(c, op, TR_STORED);
           fence_proxy_async_all();            // async-proxy (TMA) writes ordered before the generic-proxy release
           red_release_gpu(cnt_done, 1);       // release.gpu: no separate __threadfence (a MEMBAR.SC costs ~1 us)
           CH_TRACE(c, op, TR_RELEASED);
         }
         ptx::named_bar_sync(bar_id, 128);          // staging buffer free before the next item writes it
-        if (sums_out && last_s[c]) {
-          // every tile of sample n has added its sums (acquired by the counter increment above, made visible to
-          // the warpgroup by the barrier): evaluate the gate once, then raise the counter to tiles + 1
-          if (flags & SRB_CHAIN_POOL_OUT) gate_fwd();
-          else gate_bwd();
-          ptx::named_bar_sync(bar_id, 128);
-          if (store_thread) red_release_gpu(cnt_part, 1);
-        }
       }
     }
   }
@@ -1053,7 +863,7 @@ extern "C" int srb_conv_chain(srb_ctx* ctx, const srb_chain_desc* d, void* strea
     used[sp] = true;
     return 0;
   };
-  bool any_conv = false, any_gate_in = false, any_e2 = false;
+  bool any_conv = false;
   for (int i = 0; i < d->n_ops; ++i) {
     const srb_chain_op& o = d->ops[i];
     p.ops[i] = o;
@@ -1071,39 +881,8 @@ extern "C" int srb_conv_chain(srb_ctx* ctx, const srb_chain_desc* d, void* strea
       SRB_REQUIRE((m || r) || o.e == SRB_CHAIN_NONE, "srb_conv_chain: op %d has an operand tile but no MASK/RESIDUAL flag", i);
       SRB_REQUIRE(!(o.flags & SRB_COLSUM) || (o.colsum && (o.colsum_groups == 1 || o.colsum_groups == d->N)),
                   "srb_conv_chain: op %d: COLSUM needs a pointer and groups in {1, N}", i);
-      SRB_REQUIRE((o.e2 != SRB_CHAIN_NONE) == ((o.flags & (SRB_CHAIN_CA_BWD_FUSED | SRB_CHAIN_PROD_OUT)) != 0),
-                  "srb_conv_chain: op %d: a second operand tile goes with CA_BWD_FUSED / PROD_OUT and only with them", i);
-      if (o.flags & SRB_CHAIN_POOL_OUT) {
-        SRB_REQUIRE((o.flags & SRB_COLSUM) && o.colsum_groups == d->N && !(o.flags & (SRB_CHAIN_CA | SRB_CHAIN_CA_BWD_FUSED)),
-                    "srb_conv_chain: op %d: POOL_OUT needs COLSUM per sample and excludes the fused CA forms", i);
-        SRB_REQUIRE(o.ca_w1 && o.ca_b1 && o.ca_w2 && o.ca_b2 && o.ca_s && o.ca_y && o.ca_cr >= 1 && o.ca_cr <= kMaxCr,
-                    "srb_conv_chain: op %d: POOL_OUT gate parameters missing or Cr outside [1,%d]", i, kMaxCr);
-      }
-      if (o.flags & SRB_CHAIN_PROD_OUT) {
-        SRB_REQUIRE(!(o.flags & (SRB_COLSUM | SRB_CHAIN_CA | SRB_CHAIN_CA_BWD_FUSED | SRB_CHAIN_POOL_OUT)) && o.ca_scratch,
-                    "srb_conv_chain: op %d: PROD_OUT needs ca_scratch and excludes COLSUM / CA / POOL_OUT", i);
-        SRB_REQUIRE(o.ca_w1 && o.ca_b1 && o.ca_w2 && o.ca_b2 && o.ca_s && o.ca_y && o.ca_dw1 && o.ca_db1 && o.ca_dw2 &&
-                        o.ca_db2 && o.ca_cr >= 1 && o.ca_cr <= kMaxCr,
-                    "srb_conv_chain: op %d: PROD_OUT gate pointers missing or Cr outside [1,%d]", i, kMaxCr);
-        if ((rc = check_ref(o.e2, true, "saved t", i))) return rc;
-      }
-      if (o.flags & (SRB_CHAIN_GATE_IN | SRB_CHAIN_GATE_BWD_IN)) {
-        const bool f = (o.flags & SRB_CHAIN_GATE_IN) != 0;
-        SRB_REQUIRE(!(f && (o.flags & SRB_CHAIN_GATE_BWD_IN)), "srb_conv_chain: op %d: GATE_IN and GATE_BWD_IN are exclusive", i);
-        SRB_REQUIRE(i > 0 && d->ops[i - 1].kind == SRB_CHAIN_CONV &&
-                        (d->ops[i - 1].flags & (f ? SRB_CHAIN_POOL_OUT : SRB_CHAIN_PROD_OUT)),
-                    "srb_conv_chain: op %d: a gated input needs op %d to publish its sums (POOL_OUT / PROD_OUT)", i, i - 1);
-        SRB_REQUIRE(o.ca_y && o.ca_y == d->ops[i - 1].ca_y && (f || o.pool_in == d->ops[i - 1].ca_scratch),
-                    "srb_conv_chain: op %d: ca_y (and pool_in, backward) must be the buffers op %d publishes", i, i - 1);
-        SRB_REQUIRE(!(o.flags & (SRB_CHAIN_CA | SRB_CHAIN_CA_BWD_FUSED)), "srb_conv_chain: op %d: gated input excludes the fused CA forms", i);
-        if ((rc = check_ref(o.y2, true, "gated tile output", i))) return rc;
-        if (f) {
-          if ((rc = check_ref(o.xs, true, "skip window", i))) return rc;
-          SRB_REQUIRE(o.e2 == SRB_CHAIN_NONE, "srb_conv_chain: op %d: GATE_IN's second window occupies the e2 tile", i);
-          any_gate_in = true;
-        }
-      }
-      if (o.e2 != SRB_CHAIN_NONE) any_e2 = true;
+      SRB_REQUIRE((o.e2 != SRB_CHAIN_NONE) == ((o.flags & SRB_CHAIN_CA_BWD_FUSED) != 0),
+                  "srb_conv_chain: op %d: a second operand tile goes with CA_BWD_FUSED and only with it", i);
       if (o.flags & SRB_CHAIN_CA_BWD_FUSED) {
         SRB_REQUIRE(sample_sync_ok, "srb_conv_chain: op %d: CA ops need tiles_per_sample (%d) <= 2 x grid (%d); use srb_ca_bwd", i,
                     p.tiles_per_sample, grid_for_check);
@@ -1136,8 +915,6 @@ extern "C" int srb_conv_chain(srb_ctx* ctx, const srb_chain_desc* d, void* strea
     }
   }
   SRB_REQUIRE(!any_conv || (d->weights && d->n_layers > 0), "srb_conv_chain: conv ops need a filter bank");
-  // GATE_IN's second window spills 6.5 KB into the e2 tile's shared memory
-  SRB_REQUIRE(!(any_gate_in && any_e2), "srb_conv_chain: GATE_IN ops and second operand tiles cannot share a chain");
 
   for (int s = 0; s < 4; ++s) {
     if (!used[s]) {

@@ -19,6 +19,7 @@
 // one layer's dW is only 64x64x9.  The backward pass defers its weight gradients into such batches
 // (srb200/functional.py WgradQueue): they are off the critical path of the dgrad chain.
 #include <stdlib.h>
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -304,28 +305,65 @@ int srb_wgrad_umma_batched(srb_ctx* ctx, const srb_wgrad_desc* descs, const void
   }
   const int total = (int)blocks.size();
   if (total == 0) return 0;
-  // Group the blocks into launches of <= kMaxBlocks and give every block a number of CTAs
-  // proportional to its share of the launch's pixel tiles (one CTA per SM overall): a 192x192 tail
-  // layer has 16x the tiles of a 48x48 body layer and must not be left to one or two SMs.
+  // Group the blocks into launches of <= kMaxBlocks and split every block over S CTAs (each takes every S-th
+  // pixel tile) so that all CTAs of a launch carry about the same work and a launch fills the SMs once:
+  //   * blocks are sorted by cost (pixel tiles; a 1x1 block issues 8 of the 40 MMAs per tile), so the few big
+  //     layers (192x192 tail: 16x the tiles of a 48x48 body layer) meet in one launch;
+  //   * launches are packed with S_b = ceil(cost_b / T), T = half the cost of the most common block, until the
+  //     CTAs would exceed the SM count — 74 body layers x 2 CTAs, or the big layers + as many body layers as fit;
+  //   * within a launch T is then lowered as far as sum(S_b) <= #SMs allows (few blocks: many CTAs each).
+  // (Proportional rounding inside fixed 74-block launches left the first RCAN launch — tail, up-sampling and 65
+  // body layers — at 116 CTAs with 1.44x the work on the body layers' CTAs: 538 us, 60 % of the SM cycles active.)
+  auto cost = [](const WgradBlock& B) -> long long { return (long long)B.ntiles * (B.k1 ? 3 : 10); };
+  std::stable_sort(blocks.begin(), blocks.end(), [&](const WgradBlock& x, const WgradBlock& y) { return cost(x) > cost(y); });
+  auto ctas_for = [&](const WgradBlock& B, long long T) -> int {
+    long long sb = (cost(B) + T - 1) / T;
+    if (sb < 1) sb = 1;
+    if (sb > B.ntiles) sb = B.ntiles;
+    if (sb > 96) sb = 96;
+    return (int)sb;
+  };
+  long long mode_cost = cost(blocks[0]);
+  {
+    int best = 0, run = 0;
+    for (int b = 0; b < total; ++b) {          // sorted: equal costs are adjacent
+      run = (b > 0 && cost(blocks[b]) == cost(blocks[b - 1])) ? run + 1 : 1;
+      if (run > best) {
+        best = run;
+        mode_cost = cost(blocks[b]);
+      }
+    }
+  }
+  const long long T_pack = mode_cost / 2 > 0 ? (mode_cost + 1) / 2 : 1;
   bool any_split = false;
   std::vector<int> launch_start;
-  for (int b0 = 0; b0 < total; b0 += kMaxBlocks) {
+  for (int b0 = 0; b0 < total;) {
     launch_start.push_back(b0);
-    const int nb = total - b0 < kMaxBlocks ? total - b0 : kMaxBlocks;
-    long long tiles = 0;
-    for (int b = 0; b < nb; ++b) tiles += blocks[b0 + b].ntiles;
+    int nb = 0, ctas = 0;
+    while (b0 + nb < total && nb < kMaxBlocks) {
+      const int sb = ctas_for(blocks[b0 + nb], T_pack);
+      if (nb > 0 && ctas + sb > ctx->num_sms) break;
+      ctas += sb;
+      ++nb;
+    }
+    // smallest T whose CTA count still fits the SMs
+    long long lo = 1, hi = cost(blocks[b0]);
+    while (lo < hi) {
+      const long long mid = (lo + hi) / 2;
+      long long sum = 0;
+      for (int b = 0; b < nb; ++b) sum += ctas_for(blocks[b0 + b], mid);
+      if (sum <= ctx->num_sms) hi = mid;
+      else lo = mid + 1;
+    }
     int cta = 0;
     for (int b = 0; b < nb; ++b) {
       WgradBlock& B = blocks[b0 + b];
-      long long s = ((long long)B.ntiles * ctx->num_sms + tiles / 2) / (tiles > 0 ? tiles : 1);
-      if (s < 1) s = 1;
-      if (s > B.ntiles) s = B.ntiles;
-      if (s > 96) s = 96;
-      B.S = (int)s;
+      B.S = ctas_for(B, lo);
       B.cta0 = cta;
       cta += B.S;
       if (B.S > 1) any_split = true;
     }
+    b0 += nb;
   }
   if (any_split) {
     // split reductions add into dW with red.global.add, so overwritten layers start from zero
@@ -338,7 +376,7 @@ int srb_wgrad_umma_batched(srb_ctx* ctx, const srb_wgrad_desc* descs, const void
   int rc = 0;
   for (size_t li = 0; li < launch_start.size() && rc == 0; ++li) {
     const int b0 = launch_start[li];
-    const int nb = total - b0 < kMaxBlocks ? total - b0 : kMaxBlocks;
+    const int nb = (li + 1 < launch_start.size() ? launch_start[li + 1] : total) - b0;
     for (int b = 0; b < nb; ++b) P->blk[b] = blocks[b0 + b];
     P->nblocks = nb;
     const int ctas = P->blk[nb - 1].cta0 + P->blk[nb - 1].S;

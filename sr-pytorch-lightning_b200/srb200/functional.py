@@ -221,14 +221,6 @@ def chain_enabled() -> bool:
     return os.environ.get("SRB200_NO_CHAIN", "0") in ("", "0")
 
 
-def gate_deferred() -> bool:
-    """RCAN chains apply each CALayer gate inside the NEXT conv's input window (SRB_CHAIN_GATE_IN /
-    GATE_BWD_IN, include/srb200.h) so that the sample-wide reduction overlaps the halo exchange;
-    SRB200_CHAIN_GATE=0 selects the older form that waits for the reduction inside the producing op."""
-    import os
-    return os.environ.get("SRB200_CHAIN_GATE", "1") not in ("", "0")
-
-
 def _zeroed_grad_target(p):
     """Like _grad_target for gradients the kernels ACCUMULATE with atomics: the buffer is zero
     unless it is a live slice of the flat gradient buffer."""
@@ -265,31 +257,13 @@ class RCANGroupFn(Function):
         ref = ops.Chain.ref
         xin = ref(2, 0)
         cur = xin
-        if gate_deferred():
-            # conv2 of RCAB b only publishes its pool; the gate, `* y` and `+ x` (rcan.py:28,54) happen in the
-            # input window of the conv that consumes the block output (conv1 of RCAB b+1 / the group's tail
-            # conv), which also stores that output (slot 3b+2) for the skip after it and for backward
-            pending = None
-            for b in range(nb):
-                w1, b1, w2, b2, cw1, cb1, cw2, cb2 = (t.detach() for t in params[8 * b:8 * b + 8])
-                if pending is None:
-                    ch.conv(cur, ref(0, 3 * b), 2 * b, b1, relu=True)
-                else:
-                    ch.conv(ref(0, 3 * b - 2), ref(0, 3 * b), 2 * b, b1, relu=True, gate_in=pending)
-                    cur = ref(0, 3 * b - 1)
-                ch.conv(ref(0, 3 * b), ref(0, 3 * b + 1), 2 * b + 1, b2, colsum=pool[b], colsum_groups=n,
-                        pool_out=dict(w1=cw1.reshape(cw1.shape[0], 64), b1=cb1, w2=cw2.reshape(64, cw2.shape[1]), b2=cb2,
-                                      s=s_all[b], y=y_all[b]))
-                pending = dict(skip=cur, out=ref(0, 3 * b + 2), y=y_all[b])
-            ch.conv(ref(0, 3 * nb - 2), ref(0, 3 * nb), 2 * nb, params[-1].detach(), res=xin, gate_in=pending)
-        else:
-            for b in range(nb):
-                w1, b1, w2, b2, cw1, cb1, cw2, cb2 = (t.detach() for t in params[8 * b:8 * b + 8])
-                ch.conv(cur, ref(0, 3 * b), 2 * b, b1, relu=True)
-                ch.conv_ca(ref(0, 3 * b), ref(0, 3 * b + 1), ref(0, 3 * b + 2), cur, 2 * b + 1, b2, pool[b],
-                           cw1.reshape(cw1.shape[0], 64), cb1, cw2.reshape(64, cw2.shape[1]), cb2, s_all[b], y_all[b])
-                cur = ref(0, 3 * b + 2)
-            ch.conv(cur, ref(0, 3 * nb), 2 * nb, params[-1].detach(), res=xin)
+        for b in range(nb):
+            w1, b1, w2, b2, cw1, cb1, cw2, cb2 = (t.detach() for t in params[8 * b:8 * b + 8])
+            ch.conv(cur, ref(0, 3 * b), 2 * b, b1, relu=True)
+            ch.conv_ca(ref(0, 3 * b), ref(0, 3 * b + 1), ref(0, 3 * b + 2), cur, 2 * b + 1, b2, pool[b],
+                       cw1.reshape(cw1.shape[0], 64), cb1, cw2.reshape(64, cw2.shape[1]), cb2, s_all[b], y_all[b])
+            cur = ref(0, 3 * b + 2)
+        ch.conv(cur, ref(0, 3 * nb), 2 * nb, params[-1].detach(), res=xin)
         ch.run(bank)
         ctx.save_for_backward(x, A, s_all, y_all, *params)
         ctx.owner, ctx.nb = owner, nb
@@ -325,44 +299,15 @@ class RCANGroupFn(Function):
                         w2=cw2.detach().reshape(64, cr), b2=cb2.detach(), s=s_all[b], y=y_all[b], dw1=dcw1.view(cr, 64),
                         db1=dcb1, dw2=dcw2.view(64, cr), db2=dcb2, scratch=scratch[b], colsum_dt=db2)
 
-        deferred = gate_deferred()
-        ca_cache = {}
-
-        def ca_once(b):
-            if b not in ca_cache:
-                ca_cache[b] = ca_args(b)      # claims the gradient targets of RCAB b: exactly once
-            return ca_cache[b]
-
-        def gate_args(b):
-            """Deferred CALayer backward of RCAB b, applied to the input window of conv2's dgrad."""
-            a = ca_once(b)
-            return dict(dt=a["dt"], ds=a["scratch"], y=a["y"], colsum_dt=a["colsum_dt"])
-
-        def prod_args(b):
-            """dgrad op that produces dL/dout of RCAB b: publishes sum(g*t), the completing tile runs the gate backward."""
-            a = ca_once(b)
-            return dict(t=a["t"], scratch=a["scratch"], w1=a["w1"], b1=a["b1"], w2=a["w2"], b2=a["b2"], s=a["s"], y=a["y"],
-                        dw1=a["dw1"], db1=a["db1"], dw2=a["dw2"], db2=a["db2"])
-
         # group tail conv: out = conv(last) + x; its input gradient is dL/dout of the last RCAB
-        if deferred:
-            ch.conv(ref(2, 0), ref(0, 3 * nb), 2 * nb, prod_out=prod_args(nb - 1))
-        else:
-            ch.conv(ref(2, 0), ref(0, 3 * nb), 2 * nb, ca_bwd=ca_args(nb - 1))
+        ch.conv(ref(2, 0), ref(0, 3 * nb), 2 * nb, ca_bwd=ca_args(nb - 1))
         wq.append((A[3 * nb - 1], g, len(params) - 2, len(params) - 1))
         gref = ref(0, 3 * nb)
         for b in range(nb - 1, -1, -1):
             b1 = params[8 * b + 1]
             db1, grads[8 * b + 1] = _zeroed_grad_target(b1)
-            if deferred:
-                # dt_b = g_b * gate + ds/HW is formed in the window of conv2's dgrad (which stores its tile to
-                # slot 3b); the dgrad of conv1 publishes sum(g * t) of the RCAB before
-                ch.conv(gref, ref(0, 3 * b + 1), 2 * b + 1, mask=ref(1, 3 * b), colsum=db1, colsum_groups=1,
-                        gate_bwd_in=gate_args(b))
-                ch.conv(ref(0, 3 * b + 1), ref(0, 3 * b + 2), 2 * b, res=gref, prod_out=prod_args(b - 1) if b > 0 else None)
-            else:
-                ch.conv(ref(0, 3 * b), ref(0, 3 * b + 1), 2 * b + 1, mask=ref(1, 3 * b), colsum=db1, colsum_groups=1)
-                ch.conv(ref(0, 3 * b + 1), ref(0, 3 * b + 2), 2 * b, res=gref, ca_bwd=ca_args(b - 1) if b > 0 else None)
+            ch.conv(ref(0, 3 * b), ref(0, 3 * b + 1), 2 * b + 1, mask=ref(1, 3 * b), colsum=db1, colsum_groups=1)
+            ch.conv(ref(0, 3 * b + 1), ref(0, 3 * b + 2), 2 * b, res=gref, ca_bwd=ca_args(b - 1) if b > 0 else None)
             wq.append((A[3 * b], B[3 * b], 8 * b + 2, None))
             wq.append((A[3 * b - 1] if b > 0 else x, B[3 * b + 1], 8 * b, None))
             gref = ref(0, 3 * b + 2)

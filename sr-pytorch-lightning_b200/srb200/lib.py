@@ -41,18 +41,17 @@ class PackItem(C.Structure):
 CHAIN_CONV, CHAIN_CA_BWD = 0, 1
 CHAIN_CA = 32
 CHAIN_CA_BWD_FUSED = 64
-CHAIN_POOL_OUT, CHAIN_PROD_OUT, CHAIN_GATE_IN, CHAIN_GATE_BWD_IN = 128, 256, 512, 1024
 CHAIN_NONE = 0xFFFF
 CHAIN_MAX_OPS = 64
 
 
 class ChainOp(C.Structure):
     _fields_ = [("kind", c_i32), ("flags", C.c_uint32), ("x", C.c_uint16), ("y", C.c_uint16), ("e", C.c_uint16),
-                ("y2", C.c_uint16), ("e2", C.c_uint16), ("xs", C.c_uint16), ("w_layer", c_i32), ("scale", c_f32),
+                ("y2", C.c_uint16), ("e2", C.c_uint16), ("reserved0", C.c_uint16), ("w_layer", c_i32), ("scale", c_f32),
                 ("colsum_groups", c_i32), ("ca_cr", c_i32), ("colsum_scale", c_f32),
                 ("bias", c_vp), ("colsum", c_vp), ("colsum2", c_vp), ("ca_w1", c_vp), ("ca_b1", c_vp), ("ca_w2", c_vp), ("ca_b2", c_vp),
                 ("ca_s", c_vp), ("ca_y", c_vp), ("ca_dw1", c_vp), ("ca_db1", c_vp), ("ca_dw2", c_vp), ("ca_db2", c_vp),
-                ("ca_scratch", c_vp), ("pool_in", c_vp)]
+                ("ca_scratch", c_vp)]
 
 
 class ChainDesc(C.Structure):

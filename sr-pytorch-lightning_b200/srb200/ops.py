@@ -501,7 +501,7 @@ class Chain:
 
     def _op(self, kind, x, y):
         o = L.ChainOp()
-        o.kind, o.x, o.y, o.e, o.y2, o.e2, o.xs = kind, x, y, L.CHAIN_NONE, L.CHAIN_NONE, L.CHAIN_NONE, L.CHAIN_NONE
+        o.kind, o.x, o.y, o.e, o.y2, o.e2 = kind, x, y, L.CHAIN_NONE, L.CHAIN_NONE, L.CHAIN_NONE
         o.scale, o.w_layer = 1.0, 0
         self.ops.append(o)
         return o
@@ -514,41 +514,12 @@ class Chain:
         return t.data_ptr()
 
     def conv(self, x, y, w_layer, bias=None, *, relu=False, scale=1.0, res=None, mask=None, colsum=None, colsum_groups=1,
-             colsum_scale=1.0, ca_bwd=None, pool_out=None, prod_out=None, gate_in=None, gate_bwd_in=None):
+             colsum_scale=1.0, ca_bwd=None):
         """ca_bwd: dict(t=ref, dt=ref, w1, b1, w2, b2, s, y, dw1, db1, dw2, db2, scratch, colsum_dt) — fuse the
-        CALayer backward of the block whose dL/dout this conv produces (SRB_CHAIN_CA_BWD_FUSED).
-
-        Deferred-gate forms (include/srb200.h).  The tile that completes a sample's sums evaluates the gate
-        once for the sample; the next conv applies it to its own input window.
-          pool_out=dict(w1, b1, w2, b2, s, y): `colsum` [N][64] is a CALayer pool; gate -> y, mean -> s.
-          gate_in=dict(skip=ref, out=ref, y): the input is x*y + skip (both read as windows); its tile is
-            also stored to `out`.
-          prod_out=dict(t=ref, scratch, w1, b1, w2, b2, s, y, dw1, db1, dw2, db2): per-sample sums of
-            (this op's output)*t -> scratch, replaced by dL/d(mean)/HW; gate parameter gradients accumulated.
-          gate_bwd_in=dict(dt=ref, ds, y, colsum_dt): the input is x*y + ds inside the image (ds = the
-            `scratch` of the op before); its tile is stored to `dt`, its column sums added to colsum_dt."""
+        CALayer backward of the block whose dL/dout this conv produces (SRB_CHAIN_CA_BWD_FUSED)."""
         o = self._op(L.CHAIN_CONV, x, y)
         if ca_bwd is not None:
             self._fill_ca_bwd(o, **ca_bwd)
-        if pool_out is not None and pool_out is not False:
-            po = pool_out
-            o.ca_cr = po["w1"].shape[0]
-            o.ca_w1, o.ca_b1, o.ca_w2, o.ca_b2 = (self._ptr(po[k]) for k in ("w1", "b1", "w2", "b2"))
-            o.ca_s, o.ca_y = self._ptr(po["s"]), self._ptr(po["y"])
-        if gate_in is not None:
-            o.xs, o.y2 = gate_in["skip"], gate_in["out"]
-            o.ca_y = self._ptr(gate_in["y"])
-        if prod_out is not None:
-            po = prod_out
-            o.e2 = po["t"]
-            self._fill_ca_params(o, po["w1"], po["b1"], po["w2"], po["b2"], po["s"], po["y"], po["dw1"], po["db1"],
-                                 po["dw2"], po["db2"], po["scratch"])
-        if gate_bwd_in is not None:
-            gb = gate_bwd_in
-            o.y2 = gb["dt"]
-            o.ca_y = self._ptr(gb["y"])
-            o.pool_in = self._ptr(gb["ds"])
-            o.colsum2 = self._ptr(gb.get("colsum_dt"))
         o.w_layer, o.scale = w_layer, float(scale)
         o.flags = (L.RELU if relu else 0) | (L.RESIDUAL if res is not None else 0) | (L.MASK if mask is not None else 0) | \
                   (L.COLSUM if colsum is not None else 0)
@@ -558,14 +529,6 @@ class Chain:
             o.e = mask
         if ca_bwd is not None:
             o.flags |= L.CHAIN_CA_BWD_FUSED
-        if pool_out is not None and pool_out is not False:
-            o.flags |= L.CHAIN_POOL_OUT
-        if prod_out is not None:
-            o.flags |= L.CHAIN_PROD_OUT
-        if gate_in is not None:
-            o.flags |= L.CHAIN_GATE_IN
-        if gate_bwd_in is not None:
-            o.flags |= L.CHAIN_GATE_BWD_IN
         o.bias = self._ptr(bias)
         o.colsum = self._ptr(colsum)
         o.colsum_groups = colsum_groups
@@ -606,14 +569,8 @@ class Chain:
         carries the dependency across the split)."""
         lib = L.load()
         n_layers = bank.numel() // CHAIN_LAYER_BYTES if bank is not None else 0
-        gated = L.CHAIN_GATE_IN | L.CHAIN_GATE_BWD_IN
-        start = 0
-        while start < len(self.ops):
-            end = min(start + L.CHAIN_MAX_OPS, len(self.ops))
-            while end < len(self.ops) and end > start + 1 and (self.ops[end].flags & gated):
-                end -= 1            # a gated op waits on the second counter of the op before it: same launch
-            seg = self.ops[start:end]
-            start = end
+        for start in range(0, len(self.ops), L.CHAIN_MAX_OPS):
+            seg = self.ops[start:start + L.CHAIN_MAX_OPS]
             arr = (L.ChainOp * len(seg))(*seg)
             d = L.ChainDesc()
             d.N, d.H, d.W, d.n_ops = self.n, self.h, self.w, len(seg)

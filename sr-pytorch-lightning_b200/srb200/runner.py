@@ -1,0 +1,116 @@
+"""Lightning-free fit / validate / predict loops around the B200 path.
+
+The reference drives its models with `LightningCLI` (/root/reference/main.py:87-93): Lightning's fit
+loop calls `SRModel.training_step` (srmodel.py:160-171) + `configure_optimizers` (:145-154), the
+validation loop calls `validation_step` (:214-232: clamp to [0,1], PSNR / SSIM per batch, mean over
+the epoch :345-373), predict calls `predict_step` (:375-380).  Lightning is not installed in this
+image, so the same three loops are provided here over plain iterables of `{'lr': ..., 'hr': ...}`
+batches (what `srdata.py:120-133` yields).  Training goes through `srb200.trainer.TrainStep` (one CUDA
+graph per step, flat fp32 parameters / Adam state, NCCL gradient all-reduce when a process group is
+initialised); validation and prediction call the model's own `validation_step` / `predict_step`.
+
+Checkpoints hold the model `state_dict` (reference layout: interchangeable with the reference's
+`.ckpt['state_dict']`) plus the flat Adam moments and step count, so a resumed run continues
+bit-identically (tests/test_runner_gpu.py).
+"""
+from __future__ import annotations
+
+from typing import Iterable
+
+import torch
+
+from .trainer import TrainStep
+
+
+class Runner:
+    def __init__(self, model, lr_shape, scale: int | None = None, *, lr: float = 1e-3, betas=(0.9, 0.999),
+                 eps: float = 1e-8, weight_decay: float = 0.0, use_graph: bool = True, process_group=None):
+        """lr_shape: (N, C, h, w) of the training batches (fixed: the step is captured once)."""
+        self.model = model
+        self.scale = int(scale if scale is not None else model._scale_factor)
+        self.lr_shape = tuple(lr_shape)
+        self.step_runner = TrainStep(model, self.lr_shape, self.scale, lr=lr, betas=betas, eps=eps,
+                                     weight_decay=weight_decay, use_graph=use_graph, process_group=process_group)
+        self._captured = False
+        self.global_step = 0
+
+    # ---- training -----------------------------------------------------------------------------
+    def _ensure_captured(self, batch):
+        if not self._captured:
+            self.step_runner.load_batch(batch['lr'], batch['hr'])
+            # warm-up steps would move the weights: capture on a copy of the state and restore it
+            flat = self.step_runner.flat
+            keep = [t.clone() for t in (flat.flat, flat.m, flat.v, flat.step_dev)]
+            self.step_runner.capture()
+            for dst, src in zip((flat.flat, flat.m, flat.v, flat.step_dev), keep):
+                dst.copy_(src)
+            self._captured = True
+
+    def fit(self, batches: Iterable[dict], epochs: int = 1, on_step=None) -> list[float]:
+        """Runs `epochs` passes over `batches`; returns the loss of every step.  `on_step(step, loss)`
+        (optional) is called with the device loss tensor (reading it synchronises)."""
+        losses = []
+        pending = []
+        for _ in range(epochs):
+            for batch in batches:
+                if tuple(batch['lr'].shape) != self.lr_shape:
+                    raise ValueError(f"batch shape {tuple(batch['lr'].shape)} differs from the captured {self.lr_shape}")
+                self._ensure_captured(batch)
+                loss = self.step_runner.step(batch['lr'], batch['hr'])
+                self.global_step += 1
+                pending.append(loss.clone())          # the graph overwrites its loss buffer every replay
+                if on_step is not None:
+                    on_step(self.global_step, pending[-1])
+        torch.cuda.synchronize()
+        losses.extend(float(t) for t in pending)
+        return losses
+
+    # ---- evaluation ---------------------------------------------------------------------------
+    def _refresh_packed(self):
+        """The captured step re-packs the bf16 / K-major weight copies BEFORE its forward, so after a step
+        they are one Adam update behind the fp32 parameters: re-pack once before evaluating."""
+        if self.step_runner.pack_table is not None:
+            self.step_runner.pack_table.run()
+
+    @torch.no_grad()
+    def validate(self, batches: Iterable[dict]) -> dict:
+        """Mean of `validation_step`'s metrics over the batches (srmodel.py:345-373)."""
+        dev = self.step_runner.device
+        self._refresh_packed()
+        sums, count = {}, 0
+        for i, batch in enumerate(batches):
+            res = self.model.validation_step({k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}, i)
+            for k, v in res.items():
+                sums[k] = sums.get(k, 0.0) + float(v)
+            count += 1
+        self.model.on_validation_epoch_end()
+        return {k: v / max(count, 1) for k, v in sums.items()}
+
+    @torch.no_grad()
+    def predict(self, batches: Iterable[dict]) -> list[torch.Tensor]:
+        dev = self.step_runner.device
+        self._refresh_packed()
+        return [self.model.predict_step({'lr': b['lr'].to(dev)}, i).cpu() for i, b in enumerate(batches)]
+
+    # ---- checkpoint / resume ------------------------------------------------------------------
+    def state(self) -> dict:
+        flat = self.step_runner.flat
+        return {"state_dict": {k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()},
+                "adam_m": flat.m.cpu().clone(), "adam_v": flat.v.cpu().clone(),
+                "adam_step": int(flat.step_dev.item()), "global_step": self.global_step}
+
+    def save_checkpoint(self, path: str):
+        torch.save(self.state(), path)
+
+    def load_checkpoint(self, path_or_state):
+        st = torch.load(path_or_state, map_location="cpu") if isinstance(path_or_state, str) else path_or_state
+        self.model.load_state_dict(st["state_dict"])            # parameters are views of the flat buffer: copied in place
+        flat = self.step_runner.flat
+        if "adam_m" in st:
+            flat.m.copy_(st["adam_m"])
+            flat.v.copy_(st["adam_v"])
+            flat.step_dev.fill_(int(st["adam_step"]))
+        self.global_step = int(st.get("global_step", 0))
+
+    def close(self):
+        self.step_runner.close()

@@ -204,117 +204,6 @@ def test_chain_conv_with_fused_ca_backward(shape):
         assert _rel(a, b) < 1e-3
 
 
-@pytest.mark.parametrize("shape", [(16, 48, 48), (2, 16, 24), (3, 20, 12), (1, 40, 9)])
-def test_chain_deferred_gate_forward(shape):
-    """POOL_OUT + GATE_IN: conv2 publishes its pool, the next conv forms out = t*gate + skip in its own
-    input window (and stores its tile), versus srb_conv + srb_ca_fwd.  The conv on top must be
-    bit-identical to srb_conv applied to the stored block output."""
-    from srb200 import lib as L, ops
-    n, h, w = shape
-    bf = torch.bfloat16
-    cr = 4
-    y1 = _rand((n, h, w, 64), seed=5).to(bf)
-    x = _rand((n, h, w, 64), seed=6).to(bf)
-    res = _rand((n, h, w, 64), seed=7).to(bf)
-    w2 = _rand((64, 64, 3, 3), 0.05, seed=8).contiguous()
-    b2 = _rand((64,), 0.1, seed=9)
-    w3 = _rand((64, 64, 3, 3), 0.05, seed=10).contiguous()
-    b3 = _rand((64,), 0.1, seed=15)
-    cw1, cb1 = _rand((cr, 64), 0.2, seed=11), _rand((cr,), 0.1, seed=12)
-    cw2, cb2 = _rand((64, cr), 0.2, seed=13), _rand((64,), 0.1, seed=14)
-    pk2, pk3 = ops.PackedWeights(), ops.PackedWeights()
-    t = torch.empty_like(x)
-    pool = torch.zeros(n, 64, device=DEV)
-    ops.conv(y1, 0, 64, pk2, w2, b2, t, 0, 64, 3, colsum=pool, colsum_groups=n)
-    out = torch.empty_like(x)
-    s = torch.empty(n, 64, device=DEV)
-    yg = torch.empty(n, 64, device=DEV)
-    ops.ca_fwd(t, x, pool, False, cw1, cb1, cw2, cb2, out, s, yg)
-    for with_res in (False, True):
-        bank = ops.FilterBank().get([(w2, pk2), (w3, pk3)], L.PACK_FWD)
-        A = torch.zeros((3, n, h, w, 64), dtype=bf, device=DEV)
-        E = torch.stack([y1, x, res]).contiguous()
-        pool2 = torch.zeros(n, 64, device=DEV)
-        s2 = torch.empty(n, 64, device=DEV)
-        yg2 = torch.empty(n, 64, device=DEV)
-        ch = ops.Chain(n, h, w, x.device)
-        ch.space(0, A)
-        ch.space(1, E)
-        ref = ops.Chain.ref
-        ch.conv(ref(1, 0), ref(0, 0), 0, b2, colsum=pool2, colsum_groups=n,
-                pool_out=dict(w1=cw1, b1=cb1, w2=cw2, b2=cb2, s=s2, y=yg2))
-        ch.conv(ref(0, 0), ref(0, 2), 1, b3, relu=not with_res, res=ref(1, 2) if with_res else None,
-                gate_in=dict(skip=ref(1, 1), out=ref(0, 1), y=yg2))
-        ch.run(bank)
-        torch.cuda.synchronize()
-        assert torch.equal(A[0], t)
-        assert _rel(pool2, pool) < 1e-5 and _rel(s2, s) < 1e-5 and _rel(yg2, yg) < 1e-5
-        assert _rel(A[1], out) < 2e-3
-        nxt = torch.empty_like(x)
-        ops.conv(A[1].contiguous(), 0, 64, pk3, w3, b3, nxt, 0, 64, 3, relu=not with_res, res=(res, 0) if with_res else None)
-        torch.cuda.synchronize()
-        assert torch.equal(A[2], nxt)
-
-
-@pytest.mark.parametrize("shape", [(16, 48, 48), (3, 20, 12), (1, 40, 9)])
-def test_chain_deferred_gate_backward(shape):
-    """PROD_OUT + GATE_BWD_IN: a dgrad-style conv publishes sum(g*t), the next conv forms
-    dt = g*gate + ds/HW in its input window (zero outside the image), stores its tile and takes its
-    column sums, versus srb_conv + srb_ca_bwd; the masked conv on top must be bit-identical to
-    srb_conv applied to the stored dt."""
-    from srb200 import lib as L, ops
-    n, h, w = shape
-    bf = torch.bfloat16
-    cr = 4
-    x = _rand((n, h, w, 64), 0.02, seed=31).to(bf)
-    res = _rand((n, h, w, 64), 0.02, seed=32).to(bf)
-    t = _rand((n, h, w, 64), seed=33).to(bf)
-    act = _rand((n, h, w, 64), seed=41).to(bf)
-    wt = _rand((64, 64, 3, 3), 0.05, seed=34).contiguous()
-    wu = _rand((64, 64, 3, 3), 0.05, seed=42).contiguous()
-    cw1, cb1 = _rand((cr, 64), 0.2, seed=35), _rand((cr,), 0.1, seed=36)
-    cw2, cb2 = _rand((64, cr), 0.2, seed=37), _rand((64,), 0.1, seed=38)
-    s = _rand((n, 64), 0.3, seed=39)
-    yg = torch.sigmoid(_rand((n, 64), seed=40))
-    pkt, pku = ops.PackedWeights(), ops.PackedWeights()
-    g = torch.empty_like(x)
-    ops.conv(x, 0, 64, pkt, wt, None, g, 0, 64, 3, res=(res, 0))
-    dt = torch.empty_like(x)
-    gr = [torch.zeros_like(p) for p in (cw1, cb1, cw2, cb2)]
-    db2 = torch.zeros(64, device=DEV)
-    ops.ca_bwd(g, t, s, yg, cw1, cb1, cw2, cb2, dt, gr[0], gr[1], gr[2], gr[3], db2, torch.zeros(n, 64, device=DEV),
-               accumulate=True, scratch_is_zero=True)
-    bank = ops.FilterBank().get([(wt, pkt), (wu, pku)], L.PACK_FWD)
-    A = torch.zeros((3, n, h, w, 64), dtype=bf, device=DEV)
-    E = torch.stack([x, res, t, act]).contiguous()
-    gr2 = [torch.zeros_like(p) for p in (cw1, cb1, cw2, cb2)]
-    db2c = torch.zeros(64, device=DEV)
-    db1c = torch.zeros(64, device=DEV)
-    scratch = torch.zeros(n, 64, device=DEV)
-    ch = ops.Chain(n, h, w, x.device)
-    ch.space(0, A)
-    ch.space(1, E)
-    ref = ops.Chain.ref
-    ch.conv(ref(1, 0), ref(0, 0), 0, None, res=ref(1, 1),
-            prod_out=dict(t=ref(1, 2), scratch=scratch, w1=cw1, b1=cb1, w2=cw2, b2=cb2, s=s, y=yg, dw1=gr2[0], db1=gr2[1],
-                          dw2=gr2[2], db2=gr2[3]))
-    ch.conv(ref(0, 0), ref(0, 2), 1, None, mask=ref(1, 3), colsum=db1c, colsum_groups=1,
-            gate_bwd_in=dict(dt=ref(0, 1), ds=scratch, y=yg, colsum_dt=db2c))
-    ch.run(bank)
-    torch.cuda.synchronize()
-    assert torch.equal(A[0], g)
-    assert _rel(A[1], dt) < 2e-3
-    assert _rel(db2c, db2) < 2e-3
-    for a, b in zip(gr2, gr):
-        assert _rel(a, b) < 1e-3
-    nxt = torch.empty_like(x)
-    db1 = torch.zeros(64, device=DEV)
-    ops.conv(A[1].contiguous(), 0, 64, pku, wu, None, nxt, 0, 64, 3, mask=(act, 0), colsum=db1, colsum_groups=1)
-    torch.cuda.synchronize()
-    assert torch.equal(A[2], nxt)
-    assert _rel(db1c, db1) < 1e-4
-
-
 def test_chain_rejects_bad_programs():
     from srb200 import lib as L, ops
     n, h, w = 1, 16, 8
@@ -331,10 +220,9 @@ def test_chain_rejects_bad_programs():
         ch.run(torch.zeros(ops.CHAIN_LAYER_BYTES, dtype=torch.uint8, device=DEV))
 
 
-@pytest.mark.parametrize("gate", ["1", "0"], ids=["deferred-gate", "fused-ca"])
 @pytest.mark.parametrize("cfg", [dict(n_resblocks=2, n_resgroups=2), dict(n_resblocks=20, n_resgroups=1),
-                                 dict(n_resblocks=23, n_resgroups=1), dict(n_resblocks=33, n_resgroups=1)])
-def test_rcan_chain_path_matches_layer_path(cfg, gate, monkeypatch):
+                                 dict(n_resblocks=23, n_resgroups=1)])
+def test_rcan_chain_path_matches_layer_path(cfg, monkeypatch):
     """Whole model, forward + L1 + backward: the chain path (default) against the per-layer path
     (SRB200_NO_CHAIN=1) on identical weights and inputs.  Both are bf16 pipelines whose conv results
     are bit-identical; CALayer gate differences (fp32 summation order, <= 1 bf16 ulp on an
@@ -348,7 +236,6 @@ def test_rcan_chain_path_matches_layer_path(cfg, gate, monkeypatch):
     x = torch.rand(4, 3, 24, 24)
     hr = torch.rand(4, 3, 96, 96)
     res = {}
-    monkeypatch.setenv("SRB200_CHAIN_GATE", gate)
     for mode in ("chain", "layers"):
         monkeypatch.setenv("SRB200_NO_CHAIN", "0" if mode == "chain" else "1")
         m = models.RCAN(**kw)
