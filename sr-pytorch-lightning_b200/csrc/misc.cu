@@ -418,6 +418,7 @@ struct ColsumItem {
   int cs, co, C, shuffle;
   float alpha;
   int first_block, ppc;        // first CTA of this item, pixels per CTA
+  int vpp;                     // 16-byte vectors per pixel: ceil(C / 8), a power of two (lanes >= C are padding)
 };
 constexpr int kColsumMaxItems = 64;
 constexpr int kColsumChunkBytes = 128 * 1024;
@@ -431,7 +432,7 @@ __global__ void __launch_bounds__(256) colsum_batched_kernel(const __grid_consta
   int ii = 0;
   while (ii + 1 < B.n && (int)blockIdx.x >= B.it[ii + 1].first_block) ++ii;
   const ColsumItem& it = B.it[ii];
-  const int vpp = it.C >> 3;                 // 16-byte vectors per pixel (power of two, <= 32)
+  const int vpp = it.vpp;                    // 16-byte vectors per pixel (power of two, <= 32)
   const int ppi = 256 / vpp;                 // pixels per CTA iteration
   const int v = threadIdx.x % vpp, pl = threadIdx.x / vpp;
   const int64_t p0 = (int64_t)((int)blockIdx.x - it.first_block) * it.ppc;
@@ -465,7 +466,9 @@ __global__ void __launch_bounds__(256) colsum_batched_kernel(const __grid_consta
 
 int srb_colsum_batched_ok(const void* x, int cs, int co, int C, int dtype) {
   if (dtype != SRB_BF16) return 0;
-  if (C < 8 || C > 256 || (C & (C - 1))) return 0;
+  if (C < 1 || C > 256) return 0;
+  const int vpp = (C + 7) / 8;               // the padded vector lanes must exist inside the pixel (RGB tensors are 8 wide)
+  if ((vpp & (vpp - 1)) || co + vpp * 8 > cs) return 0;
   if ((cs % 8) || (co % 8) || (reinterpret_cast<uintptr_t>(x) & 15)) return 0;
   return 1;
 }
@@ -492,7 +495,8 @@ int srb_colsum_batched_launch(srb_ctx* ctx, int n, const void* const* xs, const 
       it.shuffle = shuffle[k];
       it.alpha = alpha[k];
       it.first_block = blocks;
-      it.ppc = kColsumChunkBytes / (C[k] * 2);      // a multiple of the 256 / (C/8) pixels of one iteration
+      it.vpp = (C[k] + 7) / 8;
+      it.ppc = kColsumChunkBytes / (it.vpp * 16);   // a multiple of the 256 / vpp pixels of one iteration
       blocks += srb_cdiv(npix[k] > 0 ? npix[k] : 1, it.ppc);
     }
     B.n = m;

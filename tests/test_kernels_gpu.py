@@ -484,6 +484,7 @@ def test_deferred_bias_grads_share_one_launch():
         (256, 256, 0, 16, 2, False, 1.0),
         (128, 128, 0, 20, 0, True, 1.0),
         (32, 256, 96, 16, 0, False, 1.0),
+        (3, 8, 0, 32, 0, False, 1.0),          # tail conv: RGB gradient stored 8 wide
     ]
     keep, want, got = [], [], []
     c0 = L.launch_count()
