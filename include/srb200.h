@@ -138,6 +138,11 @@ int  srb_conv_wgrad_batched(srb_ctx*, const srb_wgrad_item* items, int n, void* 
 /* which kernel family (and hence which weight packing) backend AUTO resolves to */
 int  srb_conv_uses_umma(const srb_conv_desc*);
 int  srb_wgrad_uses_umma(const srb_wgrad_desc*);
+/* Diagnostics (no device needed): how srb_conv_wgrad_batched groups n tcgen05 weight-gradient blocks
+ * (64 ci x 64 co x taps of one layer; ntiles[i] 128-pixel tiles, k1[i] != 0 for a 1x1 layer) into launches
+ * on a device with num_sms SMs.  Outputs in plan order (sorted by cost): tiles_out[i] (negative: 1x1 block),
+ * launch_out[i], ctas_out[i] = CTAs that share block i (each takes every ctas_out[i]-th tile). */
+int  srb_wgrad_plan(int num_sms, int n, const int* ntiles, const int* k1, int* tiles_out, int* launch_out, int* ctas_out);
 
 /* ---- layer chains ---------------------------------------------------------------------------
  * MANY dependent 64-channel layers in ONE persistent launch.  A single 3x3 64->64 conv on a

@@ -241,6 +241,70 @@ int encode_act_map(srb_ctx* ctx, CUtensorMap* map, const void* base, int N, int 
   return 0;
 }
 
+// Launch plan of a batch (host only; also reachable without a device through srb_wgrad_plan for the CPU tests).
+void plan_launches(std::vector<WgradBlock>& blocks, int num_sms, std::vector<int>& launch_start, bool& any_split) {
+  const int total = (int)blocks.size();
+  if (total == 0) return;
+  // Group the blocks into launches of <= kMaxBlocks and split every block over S CTAs (each takes every S-th
+  // pixel tile) so that all CTAs of a launch carry about the same work and a launch fills the SMs once:
+  //   * blocks are sorted by cost (pixel tiles; a 1x1 block issues 8 of the 40 MMAs per tile), so the few big
+  //     layers (192x192 tail: 16x the tiles of a 48x48 body layer) meet in one launch;
+  //   * launches are packed with S_b = ceil(cost_b / T), T = half the cost of the most common block, until the
+  //     CTAs would exceed the SM count — 74 body layers x 2 CTAs, or the big layers + as many body layers as fit;
+  //   * within a launch T is then lowered as far as sum(S_b) <= #SMs allows (few blocks: many CTAs each).
+  // (Proportional rounding inside fixed 74-block launches left the first RCAN launch — tail, up-sampling and 65
+  // body layers — at 116 CTAs with 1.44x the work on the body layers' CTAs: 538 us, 60 % of the SM cycles active.)
+  auto cost = [](const WgradBlock& B) -> long long { return (long long)B.ntiles * (B.k1 ? 3 : 10); };
+  std::stable_sort(blocks.begin(), blocks.end(), [&](const WgradBlock& x, const WgradBlock& y) { return cost(x) > cost(y); });
+  auto ctas_for = [&](const WgradBlock& B, long long T) -> int {
+    long long sb = (cost(B) + T - 1) / T;
+    if (sb < 1) sb = 1;
+    if (sb > B.ntiles) sb = B.ntiles;
+    if (sb > 96) sb = 96;
+    return (int)sb;
+  };
+  long long mode_cost = cost(blocks[0]);
+  {
+    int best = 0, run = 0;
+    for (int b = 0; b < total; ++b) {          // sorted: equal costs are adjacent
+      run = (b > 0 && cost(blocks[b]) == cost(blocks[b - 1])) ? run + 1 : 1;
+      if (run > best) {
+        best = run;
+        mode_cost = cost(blocks[b]);
+      }
+    }
+  }
+  const long long T_pack = mode_cost / 2 > 0 ? (mode_cost + 1) / 2 : 1;
+  for (int b0 = 0; b0 < total;) {
+    launch_start.push_back(b0);
+    int nb = 0, ctas = 0;
+    while (b0 + nb < total && nb < kMaxBlocks) {
+      const int sb = ctas_for(blocks[b0 + nb], T_pack);
+      if (nb > 0 && ctas + sb > num_sms) break;
+      ctas += sb;
+      ++nb;
+    }
+    // smallest T whose CTA count still fits the SMs
+    long long lo = 1, hi = cost(blocks[b0]);
+    while (lo < hi) {
+      const long long mid = (lo + hi) / 2;
+      long long sum = 0;
+      for (int b = 0; b < nb; ++b) sum += ctas_for(blocks[b0 + b], mid);
+      if (sum <= num_sms) hi = mid;
+      else lo = mid + 1;
+    }
+    int cta = 0;
+    for (int b = 0; b < nb; ++b) {
+      WgradBlock& B = blocks[b0 + b];
+      B.S = ctas_for(B, lo);
+      B.cta0 = cta;
+      cta += B.S;
+      if (B.S > 1) any_split = true;
+    }
+    b0 += nb;
+  }
+}
+
 }  // namespace
 
 int srb_wgrad_umma_ok(const srb_wgrad_desc* d) {
@@ -305,66 +369,9 @@ int srb_wgrad_umma_batched(srb_ctx* ctx, const srb_wgrad_desc* descs, const void
   }
   const int total = (int)blocks.size();
   if (total == 0) return 0;
-  // Group the blocks into launches of <= kMaxBlocks and split every block over S CTAs (each takes every S-th
-  // pixel tile) so that all CTAs of a launch carry about the same work and a launch fills the SMs once:
-  //   * blocks are sorted by cost (pixel tiles; a 1x1 block issues 8 of the 40 MMAs per tile), so the few big
-  //     layers (192x192 tail: 16x the tiles of a 48x48 body layer) meet in one launch;
-  //   * launches are packed with S_b = ceil(cost_b / T), T = half the cost of the most common block, until the
-  //     CTAs would exceed the SM count — 74 body layers x 2 CTAs, or the big layers + as many body layers as fit;
-  //   * within a launch T is then lowered as far as sum(S_b) <= #SMs allows (few blocks: many CTAs each).
-  // (Proportional rounding inside fixed 74-block launches left the first RCAN launch — tail, up-sampling and 65
-  // body layers — at 116 CTAs with 1.44x the work on the body layers' CTAs: 538 us, 60 % of the SM cycles active.)
-  auto cost = [](const WgradBlock& B) -> long long { return (long long)B.ntiles * (B.k1 ? 3 : 10); };
-  std::stable_sort(blocks.begin(), blocks.end(), [&](const WgradBlock& x, const WgradBlock& y) { return cost(x) > cost(y); });
-  auto ctas_for = [&](const WgradBlock& B, long long T) -> int {
-    long long sb = (cost(B) + T - 1) / T;
-    if (sb < 1) sb = 1;
-    if (sb > B.ntiles) sb = B.ntiles;
-    if (sb > 96) sb = 96;
-    return (int)sb;
-  };
-  long long mode_cost = cost(blocks[0]);
-  {
-    int best = 0, run = 0;
-    for (int b = 0; b < total; ++b) {          // sorted: equal costs are adjacent
-      run = (b > 0 && cost(blocks[b]) == cost(blocks[b - 1])) ? run + 1 : 1;
-      if (run > best) {
-        best = run;
-        mode_cost = cost(blocks[b]);
-      }
-    }
-  }
-  const long long T_pack = mode_cost / 2 > 0 ? (mode_cost + 1) / 2 : 1;
   bool any_split = false;
   std::vector<int> launch_start;
-  for (int b0 = 0; b0 < total;) {
-    launch_start.push_back(b0);
-    int nb = 0, ctas = 0;
-    while (b0 + nb < total && nb < kMaxBlocks) {
-      const int sb = ctas_for(blocks[b0 + nb], T_pack);
-      if (nb > 0 && ctas + sb > ctx->num_sms) break;
-      ctas += sb;
-      ++nb;
-    }
-    // smallest T whose CTA count still fits the SMs
-    long long lo = 1, hi = cost(blocks[b0]);
-    while (lo < hi) {
-      const long long mid = (lo + hi) / 2;
-      long long sum = 0;
-      for (int b = 0; b < nb; ++b) sum += ctas_for(blocks[b0 + b], mid);
-      if (sum <= ctx->num_sms) hi = mid;
-      else lo = mid + 1;
-    }
-    int cta = 0;
-    for (int b = 0; b < nb; ++b) {
-      WgradBlock& B = blocks[b0 + b];
-      B.S = ctas_for(B, lo);
-      B.cta0 = cta;
-      cta += B.S;
-      if (B.S > 1) any_split = true;
-    }
-    b0 += nb;
-  }
+  plan_launches(blocks, ctx->num_sms, launch_start, any_split);
   if (any_split) {
     // split reductions add into dW with red.global.add, so overwritten layers start from zero
     for (int i = 0; i < n_items; ++i)
@@ -404,5 +411,31 @@ int srb_wgrad_umma(srb_ctx* ctx, const srb_wgrad_desc* d, const void* x, const v
   if (dbias)  // bias gradient = per-channel sums of gy (gy's channel order -> parameter order)
     return srb_colsum_launch(ctx, gy, d->g_cs, d->g_co, d->Cout, (int64_t)d->N * d->H * d->W, d->dtype, dbias,
                              d->accumulate, d->alpha, d->shuffle, st);
+  return 0;
+}
+
+// Diagnostics / CPU tests: the launch plan for blocks of ntiles[i] pixel tiles (k1[i] != 0: 1x1 layer) on a device of
+// num_sms SMs.  Outputs are in plan order (blocks sorted by cost): tiles_out / launch_out / ctas_out [n].
+extern "C" int srb_wgrad_plan(int num_sms, int n, const int* ntiles, const int* k1, int* tiles_out, int* launch_out,
+                              int* ctas_out) {
+  SRB_REQUIRE(num_sms >= 1 && n >= 0 && (n == 0 || (ntiles && k1 && tiles_out && launch_out && ctas_out)),
+              "srb_wgrad_plan: bad argument");
+  std::vector<WgradBlock> blocks((size_t)n);
+  for (int i = 0; i < n; ++i) {
+    SRB_REQUIRE(ntiles[i] >= 1, "srb_wgrad_plan: block %d has %d tiles", i, ntiles[i]);
+    blocks[i].ntiles = ntiles[i];
+    blocks[i].k1 = k1[i] ? 1 : 0;
+  }
+  std::vector<int> launch_start;
+  bool any_split = false;
+  plan_launches(blocks, num_sms, launch_start, any_split);
+  for (size_t li = 0; li < launch_start.size(); ++li) {
+    const int b1 = li + 1 < launch_start.size() ? launch_start[li + 1] : n;
+    for (int b = launch_start[li]; b < b1; ++b) {
+      tiles_out[b] = blocks[b].ntiles * (blocks[b].k1 ? -1 : 1);     // negative: 1x1 block
+      launch_out[b] = (int)li;
+      ctas_out[b] = blocks[b].S;
+    }
+  }
   return 0;
 }

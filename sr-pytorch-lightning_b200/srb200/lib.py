@@ -80,6 +80,7 @@ PROTOTYPES = {
     "srb_conv_wgrad_batched": (c_i32, [c_vp, C.POINTER(WgradItem), c_i32, c_vp]),
     "srb_conv_uses_umma": (c_i32, [C.POINTER(ConvDesc)]),
     "srb_wgrad_uses_umma": (c_i32, [C.POINTER(WgradDesc)]),
+    "srb_wgrad_plan": (c_i32, [c_i32, c_i32] + [C.POINTER(c_i32)] * 5),
     "srb_conv_chain": (c_i32, [c_vp, C.POINTER(ChainDesc), c_vp]),
     "srb_conv_chain_grid": (c_i32, [c_vp, c_i32, c_i32, c_i32]),
     "srb_ca_fwd": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32] + [c_vp] * 8),
