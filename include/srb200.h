@@ -204,6 +204,9 @@ typedef struct srb_chain_desc {
   int32_t n_layers;
   int32_t* counters;
   int64_t* trace;                     /* diagnostics or NULL: [grid][2][n_ops][8] event times (ns) + [grid][4] (ns, clock) at start/end, see conv_chain.cu */
+  int32_t* tile_flags;                /* NULL: layers are ordered by the per-sample counters; else n_ops * N * tiles int32, zero on
+                                         entry (tiles = ceil(H/16) * ceil(W/8)): a tile waits only for the 3x3 neighbourhood of
+                                         tiles of the previous op */
 } srb_chain_desc;
 int  srb_conv_chain(srb_ctx*, const srb_chain_desc*, void* stream);
 /* number of CTAs srb_conv_chain launches for this shape (size of the trace buffer's first dim) */

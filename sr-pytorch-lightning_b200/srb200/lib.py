@@ -57,7 +57,7 @@ class ChainOp(C.Structure):
 class ChainDesc(C.Structure):
     _fields_ = [("N", c_i32), ("H", c_i32), ("W", c_i32), ("n_ops", c_i32), ("ops", C.POINTER(ChainOp)),
                 ("space_base", c_vp * 4), ("space_slots", c_i32 * 4), ("weights", c_vp), ("n_layers", c_i32),
-                ("counters", c_vp), ("trace", c_vp)]
+                ("counters", c_vp), ("trace", c_vp), ("tile_flags", c_vp)]
 
 
 class WgradItem(C.Structure):
