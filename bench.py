@@ -38,8 +38,8 @@ for p in (ROOT, PKG):
 import torch  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one conv_chain_kernel launch (ncu --set full,
-# profiles/r01_ncu_conv_chain_v4.txt); None until that capture exists
-CHAIN_TRAFFIC_BYTES = 247.3e6
+# profiles/r01_ncu_conv_chain_v8.txt: 12.8 MB read + 232.2 MB written); None until that capture exists
+CHAIN_TRAFFIC_BYTES = 245.0e6
 
 METRIC = "RCAN x4 train patches/sec (16x 48x48 LR patches per GPU per step, fwd+L1+bwd+Adam)"
 
@@ -392,7 +392,7 @@ def run_ours(args):
                      "us_per_launch": k_us, "us_forward_launch": k_us_f, "us_backward_launch": k_us_b,
                      "flop_per_launch": k_flop, "launches_per_step": 20,
                      "share_of_step": (10.0 * (k_us_f + k_us_b) / (ms_step * 1e3)) if args.model == "rcan" else None,
-                     "traffic_note": "dram__bytes_read+write per launch from profiles/r01_ncu_conv_chain_v4.txt",
+                     "traffic_note": "dram__bytes_read+write per launch from profiles/r01_ncu_conv_chain_v8.txt",
                      "peak_source": peaks["source"]},
         "roofline_step": {"bound": "tensor", "achieved": step_tflops, "peak": peaks["sustained"], "unit": "TFLOP/s",
                           "frac": step_tflops / peaks["sustained"],

@@ -106,7 +106,9 @@ class TrainStep:
                 ops.invalidate_packed()               # (warm-up) re-pack lazily, conv by conv
             sr = self.model.forward(self.x)
             loss = F200.l1_loss(sr, self.hr)
-            with ops.deferred_wgrads():               # weight gradients batched, off the dgrad chain
+            # weight gradients batched, off the dgrad chain; ONE flush for the whole step, so that the launch planner
+            # (wgrad_umma.cu plan_launches) sees every layer and leaves at most one partially filled launch
+            with ops.deferred_wgrads(max_items=4096):
                 loss.backward()
             if self.world > 1:
                 dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.pg)

@@ -220,9 +220,10 @@ def test_chain_rejects_bad_programs():
         ch.run(torch.zeros(ops.CHAIN_LAYER_BYTES, dtype=torch.uint8, device=DEV))
 
 
+@pytest.mark.parametrize("tile_flags", ["1", "0"], ids=["tile-flags", "sample-counters"])
 @pytest.mark.parametrize("cfg", [dict(n_resblocks=2, n_resgroups=2), dict(n_resblocks=20, n_resgroups=1),
                                  dict(n_resblocks=23, n_resgroups=1)])
-def test_rcan_chain_path_matches_layer_path(cfg, monkeypatch):
+def test_rcan_chain_path_matches_layer_path(cfg, tile_flags, monkeypatch):
     """Whole model, forward + L1 + backward: the chain path (default) against the per-layer path
     (SRB200_NO_CHAIN=1) on identical weights and inputs.  Both are bf16 pipelines whose conv results
     are bit-identical; CALayer gate differences (fp32 summation order, <= 1 bf16 ulp on an
@@ -236,6 +237,7 @@ def test_rcan_chain_path_matches_layer_path(cfg, monkeypatch):
     x = torch.rand(4, 3, 24, 24)
     hr = torch.rand(4, 3, 96, 96)
     res = {}
+    monkeypatch.setenv("SRB200_CHAIN_TILEFLAGS", tile_flags)     # both layer-ordering protocols of the chain kernel
     for mode in ("chain", "layers"):
         monkeypatch.setenv("SRB200_NO_CHAIN", "0" if mode == "chain" else "1")
         m = models.RCAN(**kw)
