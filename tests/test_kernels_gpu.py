@@ -510,7 +510,7 @@ def test_deferred_bias_grads_share_one_launch():
     assert n_launch <= 3, n_launch     # one column-sum launch + the batched weight-gradient launch(es)
 
 
-@pytest.mark.parametrize("shape", [(64, 64, 3), (256, 64, 3), (64, 576, 1), (64, 40, 3), (3, 64, 3), (64, 3, 3)])
+@pytest.mark.parametrize("shape", [(64, 64, 3), (256, 64, 3), (64, 576, 1), (64, 40, 3), (3, 64, 3), (64, 3, 3), (128, 192, 3), (256, 256, 3)])
 def test_pack_table_matches_pack_weight(shape):
     """srb_pack_table (one launch re-packing many weights, used once per optimizer step) must write
     exactly the bytes srb_pack_weight writes, for every packing / mode / shuffle, including the
