@@ -105,7 +105,8 @@ int  srb_pack_weight(srb_ctx*, const float* w_oihw, int Cout, int Cin, int ksize
 int  srb_pack_bias(srb_ctx*, const float* bias, int Cout, int shuffle, float* out, void* stream);
 /* Re-pack MANY weights in one launch (after an optimizer step): `table` is a DEVICE array of n
  * items, built once because parameter and packed-buffer addresses are stable.  ksize == 0 marks a
- * bias item (srb_pack_bias semantics).  max_elems = largest Cout*Cin*k*k in the table. */
+ * bias item (srb_pack_bias semantics).  max_elems = the Cout*Cin*k*k the grid rows are sized for (any value >= 1 is
+ * correct: items are processed with grid-stride loops; the median filter size of the table is the efficient choice). */
 typedef struct srb_pack_item {
   const float* src;
   void* dst;

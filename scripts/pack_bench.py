@@ -45,5 +45,5 @@ for _ in range(10):
     ts.append(e0.elapsed_time(e1) * 1e3)
 mb = (n_w * 64 * 64 * 9 * 4 * 2 + 2 * n_w * nbytes) / 1e6
 t = sorted(ts)[len(ts) // 2]
-print(f"pack_table staged={os.environ.get('SRB200_PACK_STAGED', '1')}: {t:.1f} us median of 10 for {len(rows)} items, "
+print(f"pack_table: {t:.1f} us median of 10 for {len(rows)} items, "
       f"{mb:.0f} MB -> {mb / t * 1e-3 * 1e3:.2f} TB/s   checksum {int(dst.view(torch.int16).sum().item())}")

@@ -663,7 +663,10 @@ extern "C" int srb_pack_table(srb_ctx* ctx, const srb_pack_item* table_dev, int 
   ctx->weights_dirty = 1;
   if (n == 0) return 0;
   SRB_REQUIRE(n <= 65535, "srb_pack_table: too many items (%d)", n);
-  int bx = srb_cdiv(max_elems, 256 * 4);
+  // grid.x is sized for a TYPICAL item (the caller passes the median filter size): every path of the kernel is a
+  // grid-stride loop, so larger filters take more trips; one 256-thread CTA per 2048 elements = one 16-byte packed
+  // vector per thread.  Sizing it for the largest filter launched 105 k CTAs per RCAN step, most without work.
+  int bx = srb_cdiv(max_elems, 256 * 8);
   if (bx < 1) bx = 1;
   if (bx > 64) bx = 64;
   pack_table_kernel<<<dim3(bx, n), 256, 0, S(stream)>>>(table_dev);

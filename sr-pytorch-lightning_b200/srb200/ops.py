@@ -149,7 +149,9 @@ class PackTable:
         assert dt.itemsize == C.sizeof(L.PackItem)
         arr = np.array(rows, dtype=dt)
         self.n = len(rows)
-        self.max_elems = max_elems
+        sizes = sorted(r[2] * r[3] * r[4] * r[4] for r in rows if r[4] > 0)
+        # grid rows are sized for the median filter (srb_pack_table): larger ones loop
+        self.max_elems = sizes[len(sizes) // 2] if sizes else max_elems
         self.table = torch.from_numpy(arr.view(np.uint8).copy()).to(device)
         self.device = device
 
