@@ -94,6 +94,24 @@ def test_error_behaviour():
     assert id(m.sub_mean.bias) not in ids and id(m.head[0].weight) in ids
 
 
+def test_product_path_has_no_cpu_fallback(monkeypatch):
+    """The models compute only through libsrb200: CPU tensors are refused, and a missing library is an error
+    at load time (never a silent PyTorch/oracle fallback)."""
+    import models
+    from srb200 import lib
+    for cls, kw in (("EDSR", dict(n_resblocks=1)), ("RCAN", dict(n_resblocks=1, n_resgroups=1)), ("RDN", {}), ("SRCNN", dict(scale_factor=2))):
+        m = getattr(models, cls)(**kw)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            m(torch.rand(1, 3, 8, 8))
+    src = open(os.path.join(ROOT, "sr-pytorch-lightning_b200", "srb200", "ops.py")).read() + \
+        open(os.path.join(ROOT, "sr-pytorch-lightning_b200", "srb200", "functional.py")).read()
+    assert "oracle" not in src                                  # the product never imports the test oracle
+    monkeypatch.setattr(lib, "LIB_PATH", "/nonexistent/libsrb200.so")
+    monkeypatch.setattr(lib, "_lib", None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        lib.load()
+
+
 def test_cabi_exports_every_declared_symbol():
     """The shared library loads and exports exactly the entry points the header declares."""
     from srb200 import lib
