@@ -7,6 +7,9 @@
 //     dependent launch (PDL).
 // P5  cluster co-residency (cudaOccupancyMaxActiveClusters).
 // P6  inter-CTA signalling latency through L2 (release/acquire flag ping-pong, N-CTA gather).
+// P7  distributed shared memory inside a cluster: remote store + remote mbarrier arrive ping-pong, halo exchange
+//     between ring neighbours, 64-float all-gather (round 2: per-sample cluster chains).
+//     Written in round 1 after the GPU budget was spent: compiles for sm_100a, NOT yet run.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -429,6 +432,165 @@ static void run_p6(int num_sms) {
   CK(cudaFree(dcy));
 }
 
+// ------------------------------------------------------------------------------------------------
+// P7: distributed shared memory inside a thread-block cluster (the halo exchange / CALayer all-gather of the
+//     per-sample cluster design)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t raddr, uint4 v) {
+  asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t rbar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = ptx::smem_u32(bar);
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (!ok) {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (!ok && clock64() - t0 > 4000000000ll) {      // ~2 s: a protocol bug must not hang the GPU
+      printf("P7: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned; barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// mode 0: ping-pong of an 8-byte token between rank 0 and rank `peer` (remote store + remote mbarrier arrive)
+// mode 1: halo exchange — every CTA writes `bytes` to its two ring neighbours' halo buffers (128 threads, 16-byte remote
+//         stores), each thread then arrives on the neighbour's barrier (count 256 = 2 writers x 128 threads); a round ends
+//         when the CTA's own barrier completes
+// mode 2: all-gather of 64 floats: every CTA writes its 256 bytes into slot[rank] of every CTA (64 threads), arrives once
+//         per peer (thread 0 after a CTA barrier + fence), waits for `csize` arrivals
+__global__ void __launch_bounds__(128, 1) p7_kernel(int mode, int peer, int bytes, int iters, long long* cycles) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  // two barriers, used alternately: a neighbour can be one round ahead (its arrivals for round i+1 may land before this
+  // CTA has waited for round i), but never two — so a barrier is never completed twice unobserved
+  __shared__ uint64_t bar[2];
+  const uint32_t rank = cluster_ctarank();
+  uint32_t csize;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+  const uint32_t buf = ptx::smem_u32(smem);                 // [0, 32 KB): halo-from-left | +32 KB: halo-from-right
+  const uint32_t bar_a = ptx::smem_u32(&bar[0]);
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < 2; ++b) ptx::mbar_init(&bar[b], mode == 0 ? 1 : (mode == 1 ? 256 : csize));
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  cluster_sync_all();
+  const long long t0 = clock64();
+  if (mode == 0) {
+    if (threadIdx.x == 0 && (rank == 0 || (int)rank == peer)) {
+      const uint32_t other = rank == 0 ? (uint32_t)peer : 0u;
+      const uint32_t rbuf = mapa(buf, other), rbar = mapa(bar_a, other);
+      for (int i = 0; i < iters; ++i) {
+        const int b = i & 1;
+        const uint32_t par = (uint32_t)(i >> 1) & 1u;
+        if (rank == 0) {
+          st_cluster_v4(rbuf, make_uint4(i, i, i, i));
+          mbar_arrive_remote_release(rbar + 8u * b);
+          mbar_wait_cluster(&bar[b], par);
+        } else {
+          mbar_wait_cluster(&bar[b], par);
+          st_cluster_v4(rbuf, make_uint4(i, i, i, i));
+          mbar_arrive_remote_release(rbar + 8u * b);
+        }
+      }
+    }
+  } else if (mode == 1) {
+    const uint32_t left = (rank + csize - 1) % csize, right = (rank + 1) % csize;
+    const uint32_t l_buf = mapa(buf + 32768u, left), r_buf = mapa(buf, right);      // I am the right / left neighbour there
+    const uint32_t l_bar = mapa(bar_a, left), r_bar = mapa(bar_a, right);
+    for (int i = 0; i < iters; ++i) {
+      for (int o = threadIdx.x * 16; o < bytes; o += 128 * 16) {
+        const uint4 v = make_uint4(i, o, rank, 0);
+        st_cluster_v4(l_buf + o, v);
+        st_cluster_v4(r_buf + o, v);
+      }
+      const int b = i & 1;
+      mbar_arrive_remote_release(l_bar + 8u * b);
+      mbar_arrive_remote_release(r_bar + 8u * b);
+      mbar_wait_cluster(&bar[b], (uint32_t)(i >> 1) & 1u);
+      __syncthreads();     // (a real kernel double-buffers the halo rows as well; the probe only times the protocol)
+    }
+  } else {
+    for (int i = 0; i < iters; ++i) {
+      if (threadIdx.x < 16) {
+        for (uint32_t pr = 0; pr < csize; ++pr)
+          st_cluster_v4(mapa(buf + rank * 256u + threadIdx.x * 16u, pr), make_uint4(i, rank, threadIdx.x, 0));
+      }
+      __syncthreads();
+      const int b = i & 1;
+      if (threadIdx.x == 0)
+        for (uint32_t pr = 0; pr < csize; ++pr) mbar_arrive_remote_release(mapa(bar_a, pr) + 8u * b);
+      mbar_wait_cluster(&bar[b], (uint32_t)(i >> 1) & 1u);
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) cycles[blockIdx.x] = clock64() - t0;
+  __syncthreads();
+  cluster_sync_all();      // no CTA exits while a peer may still write into its shared memory
+}
+
+static void run_p7() {
+  long long* dcy;
+  CK(cudaMalloc(&dcy, 256 * 8));
+  const int smem = 65536;
+  CK(cudaFuncSetAttribute(p7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(p7_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  auto launch = [&](int csize, int nclusters, int mode, int peer, int bytes, int iters, const char* what) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(csize * nclusters);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = csize;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CK(cudaMemset(dcy, 0, 256 * 8));
+    CK(cudaLaunchKernelEx(&cfg, p7_kernel, mode, peer, bytes, iters, dcy));
+    CK(cudaDeviceSynchronize());
+    std::vector<long long> cy(csize * nclusters);
+    CK(cudaMemcpy(cy.data(), dcy, cy.size() * 8, cudaMemcpyDeviceToHost));
+    double mx = 0;
+    for (auto c : cy) mx = c > mx ? (double)c : mx;
+    printf("P7 cluster=%d x%2d %s: %.0f cycles per %s\n", csize, nclusters, what, mx / iters / (mode == 0 ? 2 : 1),
+           mode == 0 ? "one-way hop" : "round");
+  };
+  const int iters = 2000;
+  for (int csize : {2, 6}) {
+    launch(csize, 1, 0, 1, 0, iters, "DSMEM ping-pong rank0<->rank1 (16-byte remote store + remote mbarrier arrive)");
+    if (csize > 2) launch(csize, 1, 0, csize - 1, 0, iters, "DSMEM ping-pong rank0<->last rank");
+  }
+  for (int bytes : {2048, 6144, 16384})
+    for (int ncl : {1, 16}) {
+      char what[128];
+      snprintf(what, sizeof what, "halo exchange, %5d B to each of 2 neighbours", bytes);
+      launch(6, ncl, 1, 0, bytes, iters, what);
+    }
+  for (int ncl : {1, 16}) launch(6, ncl, 2, 0, 0, iters, "all-gather of 64 floats among the 6 CTAs");
+  CK(cudaFree(dcy));
+}
+
 int main(int argc, char** argv) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
@@ -448,5 +610,6 @@ int main(int argc, char** argv) {
   if (want("p6")) run_p6(prop.multiProcessorCount);
   if (want("p4")) run_p4(prop.multiProcessorCount);
   if (want("p3")) run_p3(prop.multiProcessorCount);
+  if (want("p7")) run_p7();
   return 0;
 }
