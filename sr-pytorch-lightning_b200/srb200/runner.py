@@ -34,6 +34,37 @@ class Runner:
         self._captured = False
         self.global_step = 0
 
+    @classmethod
+    def from_config(cls, config, model: str, device="cuda", **overrides):
+        """Builds model + Runner from a reference YAML (`configs/train_default_sr.yml`) or an equivalent dict.
+
+        Honoured keys: `data.batch_size`, `data.patch_size` (the HR patch, srdata.py:57-80: LR = patch_size //
+        scale_factor), `data.scale_factor`, and `model.init_args` (channels, losses, optimizer, metrics, ...;
+        metrics this image cannot compute — piq's BRISQUE / LPIPS / MS-SSIM, FLIP — are dropped, PSNR / SSIM stay).
+        `model` is the class name the reference passes as `--model` (main.py:87-93).  Trainer / logger / callback
+        sections are Lightning glue and are ignored.  `overrides` are merged into the model's init args
+        (e.g. n_resblocks=20) except `lr`, which goes to the optimizer step."""
+        if isinstance(config, str):
+            import yaml
+            with open(config) as f:
+                config = yaml.safe_load(f)
+        import models
+        data = dict(config.get("data") or {})
+        init = dict((config.get("model") or {}).get("init_args") or {})
+        lr = float(overrides.pop("lr", 1e-3))
+        init.update(overrides)
+        scale = int(init.pop("scale_factor", data.get("scale_factor", 4)))
+        batch = int(init.pop("batch_size", data.get("batch_size", 16)))
+        patch = int(init.pop("patch_size", data.get("patch_size", 128)))
+        if "metrics" in init:
+            init["metrics"] = [m for m in init["metrics"] if m in ("PSNR", "SSIM")] or ["PSNR"]
+            init["metrics_for_pbar"] = [m for m in init.get("metrics_for_pbar", []) if m.split("/")[-1] in init["metrics"]]
+        if not hasattr(models, model) or not isinstance(getattr(models, model), type):
+            raise ValueError(f"unknown model {model!r}; available: {sorted(models.__all__)}")
+        net = getattr(models, model)(scale_factor=scale, batch_size=batch, patch_size=patch, **init).to(device)
+        channels = int(init.get("channels", 3))
+        return cls(net, (batch, channels, patch // scale, patch // scale), scale, lr=lr)
+
     # ---- training -----------------------------------------------------------------------------
     def _ensure_captured(self, batch):
         if not self._captured:
