@@ -70,7 +70,7 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (the reference's own path re-stated functionally, oracle/sr_oracle.py)
 # ------------------------------------------------------------------------------------------------
-def cpu_port_step_fn(model_key: str, batch: int):
+def cpu_port_step_fn(model_key: str, batch: int, device="cpu", autocast_bf16=False):
     from oracle import sr_oracle
     import models
     cls, kw, _ = MODEL_CFG[model_key]
@@ -79,15 +79,15 @@ def cpu_port_step_fn(model_key: str, batch: int):
     sd = {}
     params = []
     for k, v in ref_shapes.items():
-        t = v.detach().clone().float()
+        t = v.detach().clone().float().to(device)
         if not k.startswith(("sub_mean", "add_mean")):
             t.requires_grad_(True)
             params.append(t)
         sd[k] = t
     opt = torch.optim.Adam(params, lr=1e-3)
     g = torch.Generator().manual_seed(0)
-    x = torch.rand(batch, 3, LR, LR, generator=g)
-    hr = torch.rand(batch, 3, LR * 4, LR * 4, generator=g)
+    x = torch.rand(batch, 3, LR, LR, generator=g).to(device)
+    hr = torch.rand(batch, 3, LR * 4, LR * 4, generator=g).to(device)
     cfg = {"scale": 4}
     if cls == "RCAN":
         cfg.update(n_resblocks=kw["n_resblocks"], n_resgroups=kw["n_resgroups"])
@@ -99,7 +99,9 @@ def cpu_port_step_fn(model_key: str, batch: int):
 
     def step():
         opt.zero_grad(set_to_none=True)
-        loss = sr_oracle.l1_loss(fwd(x, sd, **cfg), hr)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast_bf16):
+            sr = fwd(x, sd, **cfg)
+        loss = sr_oracle.l1_loss(sr.float(), hr)
         loss.backward()
         opt.step()
         return loss.item()
@@ -141,6 +143,36 @@ def run_reference_arm(args):
         "e2e": {"value": pps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def run_library_arm(args):
+    """NOT a driver arm (informative only, `--impl library`): the same torch ops the reference modules call, run on
+    the GPU through stock PyTorch / cuDNN — fp32 (TF32 off) and bf16 autocast — i.e. what the reference itself would
+    reach on this B200 (SURVEY §8d "library bar").  One GPU, eager launches, CUDA events."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    out = {"impl": "library", "metric": metric_name(args.model), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+           "warmup": max(3, args.warmup), "higher_is_better": True, "dtype": "f32 / bf16 autocast", "data": "synthetic",
+           "config": {"workload": f"{MODEL_CFG[args.model][0]} x4 train step, oracle port on cuda:0 through torch "
+                                  f"{torch.__version__} / cuDNN {torch.backends.cudnn.version()}, eager"}}
+    for name, ac in (("fp32", False), ("bf16_autocast", True)):
+        step = cpu_port_step_fn(args.model, BATCH, device="cuda", autocast_bf16=ac)
+        for _ in range(max(3, args.warmup)):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        out[name] = {"value": BATCH / (ms / 1e3), "ms_per_step": ms}
+    out["value"] = out["bf16_autocast"]["value"]
+    print(json.dumps(out), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -415,13 +447,15 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "library"])
     ap.add_argument("--model", default="rcan", choices=list(MODEL_CFG))
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.impl == "library":
+        run_library_arm(args)
     else:
         run_ours(args)
 
