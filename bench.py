@@ -17,6 +17,7 @@ RCAN(n_feats=64, n_resblocks=20, n_resgroups=10, reduction=16, scale_factor=4), 
             with CUDA events; algorithmic FLOPs = 2*N*H*W*Cout*Cin*9
   cpu_baseline  the oracle port (torch CPU fp32, same model) on a bounded sample, rank 0, N=1
   --impl reference  times that CPU port with all host threads and prints the same line shape
+  --impl library    (informative, not a driver arm) the same torch ops on the GPU through stock PyTorch / cuDNN
 """
 from __future__ import annotations
 
