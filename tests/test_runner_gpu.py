@@ -91,8 +91,10 @@ def test_checkpoint_resume_continues_the_run(tmp_path):
         w_b = {k: v.detach().cpu().clone() for k, v in m2.state_dict().items()}
     finally:
         r2.close()
-    # split weight-gradient reductions add with atomics: order-dependent in the last fp32 bit
+    # Split weight-gradient reductions and the CALayer pool add with atomics (order-dependent in the last fp32 bit, which
+    # can flip a bf16 rounding downstream), so "identical" means far inside what a lost optimizer state would cause:
+    # without the Adam moments or step count the next updates differ by O(lr) = 1e-3 per weight, i.e. ~3e-2 relative.
     for a, b in zip(tail_a, tail_b):
-        assert abs(a - b) < 1e-5 * abs(a), (tail_a, tail_b)
+        assert abs(a - b) < 1e-4 * abs(a), (tail_a, tail_b)
     for k in w_a:
-        assert ((w_a[k].double() - w_b[k].double()).norm() <= 1e-5 * w_a[k].double().norm() + 1e-12), k
+        assert ((w_a[k].double() - w_b[k].double()).norm() <= 1e-3 * w_a[k].double().norm() + 1e-12), k
