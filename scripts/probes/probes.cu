@@ -591,6 +591,89 @@ static void run_p7() {
   CK(cudaFree(dcy));
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// P8: tcgen05.mma.cta_group::2 throughput at N = 64 / 128 (M = 256 over a CTA pair).  In SS mode a 128 x 64 x 16 MMA
+//     reads 4 KB of A + 2 KB of B from shared memory (48 cycles at 128 B/cycle against 32 of tensor work); a CTA pair
+//     shares B (each CTA holds N/2 rows of it), i.e. 5 KB per CTA and MMA -> expected 40 cycles.
+// ------------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) p8_kernel(int N, int iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  for (int i = threadIdx.x; i < (96 * 1024) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem_raw + (base - ptx::smem_u32(smem_raw)))[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(&slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  ptx::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem = slot;
+  long long t0 = 0;
+  if (rank == 0 && threadIdx.x == 0) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    const uint64_t adesc = ptx::smem_desc_sw128(base, 16u, 1024u);
+    const uint64_t bdesc = ptx::smem_desc_sw128(base + 48 * 1024, 16u, 1024u);
+    t0 = clock64();
+    for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem),
+            "l"(adesc + (uint64_t)(u * 2)), "l"(bdesc + (uint64_t)(u * 2)), "r"(idesc), "r"(1u)
+            : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     ptx::smem_u32(&bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+  }
+  if (threadIdx.x == 0) {
+    ptx::mbar_wait(&bar, 0);
+    if (rank == 0) out[blockIdx.x / 2] = clock64() - t0;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (threadIdx.x < 32) {
+    ptx::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+  }
+}
+
+static void run_p8(int num_sms) {
+  long long* dcy;
+  CK(cudaMalloc(&dcy, 256 * 8));
+  const int smem = 98 * 1024;
+  CK(cudaFuncSetAttribute(p8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int iters = 4096;
+  for (int pairs : {1, num_sms / 2})
+    for (int N : {64, 128, 256}) {
+      CK(cudaMemset(dcy, 0, 256 * 8));
+      p8_kernel<<<pairs * 2, 128, smem>>>(N, iters, dcy);
+      CK(cudaDeviceSynchronize());
+      std::vector<long long> cy(pairs);
+      CK(cudaMemcpy(cy.data(), dcy, pairs * 8, cudaMemcpyDeviceToHost));
+      double mean = 0;
+      for (auto c : cy) mean += (double)c / pairs;
+      const double cyc = mean / iters, macs = 128.0 * N * 16;   // per SM
+      printf("P8 cta_group::2 pairs=%3d M=256 N=%3d: %6.1f cyc/MMA -> %6.0f MAC/cyc/SM (%5.1f%% of 4096)\n", pairs, N, cyc,
+             macs / cyc, 100.0 * macs / cyc / 4096.0);
+    }
+  CK(cudaFree(dcy));
+}
+
 int main(int argc, char** argv) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
@@ -611,5 +694,6 @@ int main(int argc, char** argv) {
   if (want("p4")) run_p4(prop.multiProcessorCount);
   if (want("p3")) run_p3(prop.multiProcessorCount);
   if (want("p7")) run_p7();
+  if (want("p8")) run_p8(prop.multiProcessorCount);
   return 0;
 }

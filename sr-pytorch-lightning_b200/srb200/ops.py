@@ -79,7 +79,12 @@ def invalidate_packed():
 
 
 _all_packs = weakref.WeakSet()
-_managed = False   # True: a PackTable re-packs every cached entry once per step; caches never go stale
+# Addresses of the packed buffers the installed PackTable refreshes once per step (None: no table).  ONLY those
+# entries are trusted without a version check; everything else (keys first used after the table was built: a
+# validation image that takes the per-layer path, fp32 / SIMT packings, a second model) falls back to the
+# (data_ptr, _version, generation) tag, and `invalidate_packed()` — called by TrainStep.run after every step,
+# because the flat Adam kernel does not bump tensor versions — makes them re-pack on their next use.
+_managed = None
 
 
 class PackedWeights:
@@ -96,7 +101,7 @@ class PackedWeights:
         key = (packing, mode, shuffle) if out is None else (packing, mode, shuffle, "bank")
         hit = self._cache.get(key)
         same_home = hit is not None and (out is None or hit[1].data_ptr() == out.data_ptr())
-        if same_home and _managed and hit[2].data_ptr() == w.data_ptr():
+        if same_home and _managed is not None and hit[1].data_ptr() in _managed and hit[2].data_ptr() == w.data_ptr():
             return hit[1]
         tag = (w.data_ptr(), w._version, w.device, _generation)
         if same_home and hit[0] == tag:
@@ -110,7 +115,7 @@ class PackedWeights:
             return b.detach() if b is not None else None
         key = ("bias", shuffle)
         hit = self._cache.get(key)
-        if hit is not None and _managed and hit[2].data_ptr() == b.data_ptr():
+        if hit is not None and _managed is not None and hit[1].data_ptr() in _managed and hit[2].data_ptr() == b.data_ptr():
             return hit[1]
         tag = (b.data_ptr(), b._version, b.device, _generation)
         if hit is not None and hit[0] == tag:
@@ -124,8 +129,8 @@ class PackTable:
     """Device table of every (parameter -> packed buffer) pair currently cached by the model's
     PackedWeights objects; `run()` re-packs them all in one launch (srb_pack_table).  Built after
     a warm-up step, when every conv has been through forward and backward once.  While a table is
-    installed (`_managed`), cached buffers are trusted: addresses are stable and the table refreshes
-    their contents each step."""
+    installed, the buffers it lists (`_managed`) are trusted: addresses are stable and the table refreshes
+    their contents each step.  Entries created later are NOT in the table and keep the version/generation check."""
 
     def __init__(self, device):
         import numpy as np
@@ -157,12 +162,12 @@ class PackTable:
 
     def install(self):
         global _managed
-        _managed = True
+        _managed = frozenset(packed.data_ptr() for packed, _ in self.keep)
 
     @staticmethod
     def uninstall():
         global _managed
-        _managed = False
+        _managed = None
 
     def run(self):
         L.check(L.load().srb_pack_table(C.c_void_p(L.ctx(self.device.index)), _p(self.table), self.n, self.max_elems,

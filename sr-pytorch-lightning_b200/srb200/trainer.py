@@ -149,6 +149,9 @@ class TrainStep:
         self.hr.copy_(hr_batch, non_blocking=True)
 
     def run(self):
+        # the step's Adam kernel rewrites the parameters without bumping tensor versions: packed copies that the
+        # pack table does not refresh (created after capture, e.g. by a validation pass on another shape) are stale now
+        ops.invalidate_packed()
         if self.graph is not None:
             self.graph.replay()
         else:
