@@ -210,6 +210,11 @@ typedef struct srb_chain_desc {
                                          tiles of the previous op */
 } srb_chain_desc;
 int  srb_conv_chain(srb_ctx*, const srb_chain_desc*, void* stream);
+/* 1 if srb_conv_chain runs this chain with the per-sample thread-block-cluster kernel (conv_cluster.cu: H % 16 == 0,
+ * W in {24, 48}, at most 8 CTAs of 16 x 24 pixels per sample, every op a conv that consumes the previous op's result;
+ * activations stay in shared memory between layers, halos travel through distributed shared memory), 0 if it takes the
+ * L2-flag kernel (conv_chain.cu).  SRB200_CHAIN_CLUSTER=0 disables the cluster kernel. */
+int  srb_conv_chain_uses_cluster(const srb_chain_desc*);
 /* number of CTAs srb_conv_chain launches for this shape (size of the trace buffer's first dim) */
 int  srb_conv_chain_grid(const srb_ctx*, int N, int H, int W);
 

@@ -884,12 +884,19 @@ extern "C" int srb_conv_chain_grid(const srb_ctx* ctx, int N, int H, int W) {
   return chain_grid(ctx->num_sms, N, H, W);
 }
 
+// conv_cluster.cu: one thread-block cluster per sample, halos through distributed shared memory
+int srb_chain_cluster_eligible(const srb_chain_desc* d);
+int srb_chain_cluster_launch(srb_ctx* ctx, const srb_chain_desc* d, void* stream);
+
+extern "C" int srb_conv_chain_uses_cluster(const srb_chain_desc* d) { return d && d->ops ? srb_chain_cluster_eligible(d) : 0; }
+
 extern "C" int srb_conv_chain(srb_ctx* ctx, const srb_chain_desc* d, void* stream) {
   SRB_REQUIRE(ctx && d && d->ops && d->counters, "srb_conv_chain: null argument");
   SRB_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0, "srb_conv_chain: empty shape N=%d H=%d W=%d", d->N, d->H, d->W);
   SRB_REQUIRE(d->n_ops >= 1 && d->n_ops <= SRB_CHAIN_MAX_OPS, "srb_conv_chain: n_ops %d outside [1,%d]", d->n_ops,
               SRB_CHAIN_MAX_OPS);
   SRB_REQUIRE(d->N < (1 << 14), "srb_conv_chain: batch too large");
+  if (srb_chain_cluster_eligible(d)) return srb_chain_cluster_launch(ctx, d, stream);
   static_assert(sizeof(ChainParams) + sizeof(ChainMaps) < 32000, "kernel parameters exceed the 32 KB limit");
   ChainParams* pp = new ChainParams();
   ChainMaps* mm = new ChainMaps();

@@ -83,6 +83,7 @@ PROTOTYPES = {
     "srb_wgrad_plan": (c_i32, [c_i32, c_i32] + [C.POINTER(c_i32)] * 5),
     "srb_conv_chain": (c_i32, [c_vp, C.POINTER(ChainDesc), c_vp]),
     "srb_conv_chain_grid": (c_i32, [c_vp, c_i32, c_i32, c_i32]),
+    "srb_conv_chain_uses_cluster": (c_i32, [C.POINTER(ChainDesc)]),
     "srb_ca_fwd": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32] + [c_vp] * 8),
     "srb_ca_bwd": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32] + [c_vp] * 15 + [c_i32, c_i32, c_vp]),
     "srb_pack_table": (c_i32, [c_vp, c_vp, c_i32, c_i64, c_vp]),

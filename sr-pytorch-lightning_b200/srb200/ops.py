@@ -503,6 +503,7 @@ class Chain:
         self.spaces = [None] * 4
         self.ops = []
         self.keep = []
+        self.used_cluster = None      # set by run(): the per-sample cluster kernel (conv_cluster.cu) took the last launch
 
     def space(self, index: int, t: torch.Tensor):
         assert t.dim() == 5 and t.is_contiguous() and t.dtype == torch.bfloat16 and t.shape[4] == 64
@@ -608,6 +609,7 @@ class Chain:
             if trace is None:
                 trace = CHAIN_TRACE
             d.trace = trace.data_ptr() if trace is not None else None
+            self.used_cluster = bool(lib.srb_conv_chain_uses_cluster(C.byref(d)))
             L.check(lib.srb_conv_chain(C.c_void_p(L.ctx(self.device.index)), C.byref(d), _stream()), "srb_conv_chain")
 
 
