@@ -12,11 +12,13 @@
 //     X[(i + 1) & 1]: the centre with st.shared, the border pixels ALSO into the neighbours' halos with
 //     st.shared::cluster, then mbarrier.arrive.release.cluster on the neighbours' "ready" barriers (measured hop:
 //     0.30 us, profiles/r02_hw_probes_p7.txt; the L2 path it replaces: 2.8 us);
-//   * saved activations (what backward / the weight gradients need) leave as plain st.global from the epilogue
-//     registers — nothing in the kernel waits for them; residual / mask / saved-t operands come back with ld.global
-//     by the thread that owns the pixel (issued before the accumulator wait; HBM-cold ones are L2-prefetched one op
-//     ahead), so there is no operand staging in shared memory at all (conv_chain.cu's lesson: non-MMA shared-memory
-//     traffic is what an N=64 SS-mode MMA stream cannot afford);
+//   * saved activations (what backward / the weight gradients need) are copied X[out] -> global AFTER the tile has been
+//     published, by all 256 epilogue threads with 8 lanes per 128-byte pixel line (the first version stored them from
+//     the epilogue registers, one 16-byte piece per lane in 32 different lines per instruction: 32 LSU wavefronts
+//     instead of 4, and the epilogue — not the tensor pipe — set the pace: profiles/r02_cluster_trace_v1.txt);
+//   * operands: a residual that is the block input is still in X[out] and is read in place; a residual produced two ops
+//     earlier (the dL/dout chain of the backward pass) is parked in TMEM by its producer (tcgen05.st) and read back
+//     with tcgen05.ld; saved forward tensors (ReLU mask, pre-attention t) arrive as TMA tiles in one 16 KB buffer;
 //   * CALayer (rcan.py:10-29) and its backward: per-thread running sums over the CTA's three tiles, ONE warp
 //     transpose-reduce, a 64-float DSMEM all-gather among the cluster, the 64->Cr->64 gate evaluated by every CTA in
 //     the same (rank) order, then a second pass applies it.  Forward re-reads t from the accumulators still in TMEM.
@@ -24,7 +26,7 @@
 //     barriers per buffer — A: "positions 0-1 of every contributor are in" (enables position 0 of the next op),
 //     B: "everything is in" — so the next op's first tile runs under the epilogue of this op's last tile.
 // Plain conv ops issue the same MMA sequence and epilogue arithmetic as conv_chain.cu / conv_c64.cu: results are
-// bit-identical (tests/test_chain_gpu.py).
+// bit-identical (tests/test_cluster_chain_gpu.py).
 #include <type_traits>
 
 #include "common.cuh"
@@ -32,18 +34,22 @@
 
 namespace {
 
-constexpr int kThreads = 384;                       // 12 warps: misc, MMA, filters, spare, 8 x epilogue
+constexpr int kThreads = 384;                       // 12 warps: operand tiles, MMA, filters, spare, 8 x epilogue
 constexpr int kEpi = 256;
 constexpr int kXW = 26, kXH = 18;                   // activation buffer: 24 + 2 columns, 16 + 2 rows
 constexpr uint32_t kXBytes = kXH * kXW * 128u;      // 59904
 constexpr uint32_t kXStride = 60u * 1024u;
 constexpr uint32_t kSlabBytes = 3u * 64u * 128u;    // one kw slab: [kh][cout][cin]
 constexpr uint32_t kWBytes = 3u * kSlabBytes;       // 73728
-constexpr uint32_t kTmemCols = 256;                 // four 64-column accumulators, round robin
+constexpr uint32_t kEBytes = 128u * 128u;           // one operand tile
+constexpr uint32_t kTmemCols = 512;                 // 0-255: four 64-column accumulators; 256-447: two parking areas
+constexpr uint32_t kParkBase = 256, kParkArea = 96; //          (3 tiles x 32 columns of packed bf16 pairs each)
 constexpr int kMaxCr = 16;
 constexpr int kMaxCluster = 8;
 constexpr uint32_t kScaled = 1u << 16;    // epilogue specialisation keys: scale != 1 / no specialisation
 constexpr uint32_t kGeneric = 1u << 17;
+
+enum { RES_NONE = 0, RES_INPLACE = 1, RES_TMEM = 2, RES_GLOBAL = 3 };
 
 struct COp {
   uint32_t flags;
@@ -57,8 +63,11 @@ struct COp {
   float *ca_s, *ca_y, *ca_dw1, *ca_db1, *ca_dw2, *ca_db2;
   uint8_t* y;            // slot base addresses
   uint8_t* y2;
-  const uint8_t* e;      // residual or mask slot
-  const uint8_t* e2;     // saved t (CA_BWD_FUSED)
+  const uint8_t* e;      // residual slot (RES_GLOBAL)
+  uint16_t t_ref;        // operand tile by TMA: ReLU mask (MASK) or saved t (CA_BWD_FUSED); SRB_CHAIN_NONE if none
+  uint8_t res_mode;      // RES_*
+  uint8_t park;          // keep the packed result y in TMEM for the op after next (its residual)
+  uint32_t pad;
 };
 
 struct CParams {
@@ -79,10 +88,11 @@ struct CParams {
 struct CMaps {
   CUtensorMap x0;        // 5-D (c, w, h, n, slot) over the space of op 0's input, box 64 x 26 x 18
   CUtensorMap w;         // 4-D (cin, cout, tap, layer), box 64 x 64 x 3
+  CUtensorMap tile[4];   // per space: box 64 x 8 x 16 (operand tiles)
 };
 
 struct Small {
-  uint64_t w_full[3], w_empty[3], acc_full[4], acc_empty[4], x_full;
+  uint64_t w_full[3], w_empty[3], acc_full[4], acc_empty[4], x_full, e_full, e_empty;
   uint64_t ready[2][2];          // [buffer][A / B]
   uint64_t pool_full[2];
   uint32_t tmem_slot, pad;
@@ -92,7 +102,7 @@ struct Small {
   float ca_s[64], ca_y[64], ca_du[64], ca_ds[64], ca_tot[64], ca_z[kMaxCr], ca_dv[kMaxCr];
 };
 
-constexpr uint32_t kSmemBytes = kWBytes + 2u * kXStride + (uint32_t)sizeof(Small) + 1024u;
+constexpr uint32_t kSmemBytes = kWBytes + 2u * kXStride + kEBytes + (uint32_t)sizeof(Small) + 1024u;
 
 // ---- cluster / DSMEM primitives ------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -114,7 +124,8 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t raddr, uint4 v) {
 __device__ __forceinline__ void st_cluster_f32(uint32_t raddr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory");
 }
-// cumulative over everything ordered before it in this CTA (the arriving thread has been through a bar.sync with the writers)
+// release at cluster scope: cumulative over everything ordered before it in this CTA (the arriving thread has been
+// through a bar.sync with the writers) — the cluster-scope form of conv_chain.cu's red.release.gpu after a barrier
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t raddr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
@@ -140,11 +151,19 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     }
   }
 }
-// generic-proxy writes (st.shared / st.shared::cluster) ordered before async-proxy reads (tcgen05.mma operands)
-__device__ __forceinline__ void fence_proxy_async_cluster() { asm volatile("fence.proxy.async.shared::cluster;" ::: "memory"); }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-// plain (coherent) 16-byte global accesses: operands may have been written earlier in this launch BY THE SAME THREAD
-__device__ __forceinline__ uint4 ldg128(const uint8_t* p) {
+// generic-proxy writes ordered before async-proxy reads (tcgen05.mma operands).  Writers fence their LOCAL stores
+// (the standard st.shared -> fence -> barrier -> UMMA pattern); remote halo stores become visible through the
+// release/acquire pair on the consumer's ready barrier, and the consumer's MMA thread runs its own proxy fence between
+// that acquire and the MMAs.  SRB_CLUSTER_STRICT_FENCE (compile time) makes every writer fence at cluster scope too
+// (+0.4 us per tile, profiles/r02_cluster_trace_v1.txt).
+__device__ __forceinline__ void fence_writer() {
+#ifdef SRB_CLUSTER_STRICT_FENCE
+  asm volatile("fence.proxy.async.shared::cluster;" ::: "memory");
+#else
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ uint4 ldg128(const uint8_t* p) {      // plain (coherent) 16-byte global load
   uint4 v;
   asm volatile("ld.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
@@ -159,6 +178,24 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, 
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+
+// 32 lanes x 16 consecutive 32-bit columns: thread i of the warp owns lane (base_lane + i)
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // 36 MMAs of one tile (same order as conv_chain.cu mma_tile: kw slab, kh, four 16-channel k-steps)
 __device__ __forceinline__ void mma_tile(uint32_t tmem_d, uint32_t a_lo, uint32_t w_lo, uint64_t* w_full, uint64_t* w_empty,
@@ -206,6 +243,19 @@ __device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lan
   return v[0];
 }
 
+__device__ __forceinline__ void unpack4(const uint4 (&ev)[4], float (&f)[32]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const uint32_t w[4] = {ev[g].x, ev[g].y, ev[g].z, ev[g].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 t = unpack_bf16x2(w[e]);
+      f[g * 8 + e * 2] = t.x;
+      f[g * 8 + e * 2 + 1] = t.y;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__ CParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -215,7 +265,8 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
   uint8_t* base_ptr = smem_raw + (base - ptx::smem_u32(smem_raw));
   const uint32_t wbase = base;
   const uint32_t xbase = base + kWBytes;                       // X[0]; X[1] = + kXStride
-  Small& S = *reinterpret_cast<Small*>(base_ptr + kWBytes + 2u * kXStride);
+  const uint32_t ebase = xbase + 2u * kXStride;                // operand tile / staging
+  Small& S = *reinterpret_cast<Small*>(base_ptr + kWBytes + 2u * kXStride + kEBytes);
 
   const int halves = p.halves, bands = p.bands;
   const int csize = halves * bands;
@@ -236,6 +287,8 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
       ptx::mbar_init(&S.acc_empty[i], 8);
     }
     ptx::mbar_init(&S.x_full, 1);
+    ptx::mbar_init(&S.e_full, 1);
+    ptx::mbar_init(&S.e_empty, 8);
     const uint32_t nv = (has_up ? 1u : 0u) + (has_dn ? 1u : 0u);
     const uint32_t ca = 2u + 2u * nv + (has_side ? 1u + nv : 0u);
     const uint32_t cb = 3u + 3u * nv;
@@ -262,11 +315,23 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
   const float inv_hw = 1.f / (float)(p.H * p.W);
 
   if (warp == 0) {
-    // ===================== initial window: op 0's input with halo, straight from global =====================
+    // ===================== initial window + operand tiles (saved forward tensors) by TMA =====================
     if (lane == 0) {
       ptx::prefetch_tensormap(&maps.x0);
       ptx::mbar_arrive_expect_tx(&S.x_full, kXBytes);
       tma_load_5d(xbase, &maps.x0, &S.x_full, 0, f * 24 - 1, band * 16 - 1, n, p.x0_slot);
+      uint32_t e_k = 0;
+      for (int op = 0; op < p.n_ops; ++op) {
+        const uint16_t r = p.ops[op].t_ref;
+        if (r == SRB_CHAIN_NONE) continue;
+        for (int q = 0; q < 3; ++q) {
+          const int j = mirror ? 2 - q : q;
+          ptx::mbar_wait(&S.e_empty, (e_k & 1u) ^ 1u);
+          ptx::mbar_arrive_expect_tx(&S.e_full, kEBytes);
+          tma_load_5d(ebase, &maps.tile[r >> 14], &S.e_full, 0, f * 24 + 8 * j, band * 16, n, r & 0x3FFF);
+          ++e_k;
+        }
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -314,13 +379,15 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
     // ===================== epilogue: 8 warps, thread = (pixel of the tile, 32-channel half) =====================
     const int et = (int)threadIdx.x - 128;          // 0..255
     const int w8 = warp - 4;                        // 0..7
-    const int quarter = warp & 3;                   // TMEM lane quarter this warp may read
+    const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
     const int h = w8 >> 2;                          // channel half
     const int row = quarter * 32 + lane;            // pixel within the tile
     const int ty = row >> 3, tx = row & 7;
+    const uint32_t tm_lane = (uint32_t)(quarter * 32) << 16;
     // shared-memory addresses of this pixel for tile 0 of X[0] (tile j: + j * 1024, buffer 1: + kXStride)
     const uint32_t idx_l = (uint32_t)((ty + 1) * kXW + tx + 1);
     const uint32_t xl = xbase + idx_l * 128u, sw_l = idx_l & 7u;
+    const uint32_t el = ebase + (uint32_t)row * 128u;            // this pixel's row of the operand tile (swizzle = tx)
     uint32_t up_a = 0, dn_a = 0, side_a = 0, dgu_a = 0, dgd_a = 0, sw_up = 0, sw_dn = 0, sw_side = 0, sw_dg = 0;
     if (has_up && ty == 0) {
       const uint32_t idx = (uint32_t)(17 * kXW + tx + 1);
@@ -348,8 +415,16 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
         sw_dg = di & 7u;
       }
     }
-    // global byte offset of this thread's 64 bytes for tile 0 (tile j: + j * 1024)
+    // global byte offset of this thread's 64 bytes for tile 0 (tile j: + j * 1024): RES_GLOBAL operands only
     const size_t goff0 = ((((size_t)n * p.H + band * 16 + ty) * p.W) + f * 24 + tx) * 128u + (size_t)h * 64u;
+    // cooperative tile copy (shared -> global): 8 consecutive threads move one pixel's 128-byte line; thread = (16-byte
+    // chunk cc, pixel column ctx, pixel rows cty + 4k for k = 0..3).  (4 * 26) % 8 == 0, so the swizzle is the same for all k.
+    const int cc = et & 7, ctx = (et >> 3) & 7, cty = et >> 6;
+    const uint32_t cidx = (uint32_t)((cty + 1) * kXW + ctx + 1);
+    const uint32_t cx = xbase + cidx * 128u + (((uint32_t)cc ^ (cidx & 7u)) << 4);          // + j * 1024 + ob * kXStride + k * 4 * 26 * 128
+    const uint32_t ce = ebase + (uint32_t)(et >> 3) * 128u + (((uint32_t)cc ^ (uint32_t)ctx) << 4);   // + k * 32 * 128
+    const size_t cg0 = ((((size_t)n * p.H + band * 16 + cty) * p.W) + f * 24 + ctx) * 128u + (size_t)cc * 16u;   // + j * 1024 + k * 4 * W * 128
+    const size_t cg_k = (size_t)4 * p.W * 128u;
     // "ready" arrivals: lanes 0-8 of the first epilogue warp own one target each (address for buffer 0; + 16 for buffer 1)
     //   0 own A  1 own B  2 up A  3 up B  4 down A  5 down B  6 side A  7 up-diagonal A  8 down-diagonal A
     uint32_t arr_a = 0, arr_qmask = 0;
@@ -369,6 +444,7 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
     }
     const uint32_t pool_bar0 = ptx::smem_u32(&S.pool_full[0]);
     uint32_t ca_count = 0;                          // two-phase (CALayer) ops so far
+    uint32_t e_k = 0;                               // operand tiles consumed so far
 
     // write this pixel's 32 channels into X[ob] (centre + the neighbours' halos)
     auto store_x = [&](const uint32_t (&pk)[16], const int j, const int q, const int ob) {
@@ -388,12 +464,55 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
         }
       }
     };
+    // centre only (X[ob] as scratch: dL/dout before the CALayer backward rewrites it in place)
+    auto store_centre = [&](const uint32_t (&pk)[16], const int j, const int ob) {
+      const uint32_t off = (uint32_t)j * 1024u + (uint32_t)ob * kXStride;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        ptx::sts128(xl + off + (((uint32_t)(h * 4 + g) ^ sw_l) << 4), make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]));
+    };
+    auto load_centre = [&](uint4 (&ev)[4], const int j, const int ob) {
+      const uint32_t off = (uint32_t)j * 1024u + (uint32_t)ob * kXStride;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) ev[g] = ptx::lds128(xl + off + (((uint32_t)(h * 4 + g) ^ sw_l) << 4));
+    };
     // all 256 threads have written position q of X[ob]: publish to the consumers' MMA issuers
     auto publish = [&](const int q, const int ob, const int op) {
-      fence_proxy_async_cluster();
+      fence_writer();
       if (et == 0 && q == 0) CL_TRACE(op, 7);
       ptx::named_bar_sync(1, kEpi);
       if (arr_a && ((arr_qmask >> q) & 1u)) mbar_arrive_cluster(arr_a + (uint32_t)ob * 16u);
+      if (et == 0) CL_TRACE(op, q == 0 ? 8 : (q == 1 ? 10 : 12));
+    };
+    // tile j of X[ob] -> global slot (after a barrier that follows the writes): full 128-byte lines per 8 lanes
+    auto copy_out_x = [&](uint8_t* slot, const int j, const int ob) {
+      const uint32_t s0 = cx + (uint32_t)j * 1024u + (uint32_t)ob * kXStride;
+      uint8_t* g0 = slot + cg0 + (size_t)j * 1024u;
+      uint4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = ptx::lds128(s0 + (uint32_t)k * (4u * kXW * 128u));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) stg128(g0 + (size_t)k * cg_k, v[k]);
+    };
+    auto copy_out_e = [&](uint8_t* slot, const int j) {
+      uint8_t* g0 = slot + cg0 + (size_t)j * 1024u;
+      uint4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = ptx::lds128(ce + (uint32_t)k * 4096u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) stg128(g0 + (size_t)k * cg_k, v[k]);
+    };
+    // this pixel's 64 bytes of the operand tile the producer warp requested for (op, q)
+    auto take_operand = [&](uint4 (&tv)[4]) {
+      ptx::mbar_wait(&S.e_full, e_k & 1u);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) tv[g] = ptx::lds128(el + (((uint32_t)(h * 4 + g) ^ (uint32_t)tx) << 4));
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&S.e_empty);
+      ++e_k;
+    };
+    auto park_addr = [&](const int area, const int q) {
+      return tmem_acc + tm_lane + kParkBase + (uint32_t)area * kParkArea + (uint32_t)q * 32u + (uint32_t)h * 16u;
     };
     // per-thread running sums -> per-channel totals of this CTA in S.wsum; returns after a barrier
     auto reduce_cta = [&](float (&rs)[32]) {
@@ -402,10 +521,10 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
       ptx::named_bar_sync(1, kEpi);
     };
     auto cta_total = [&](const int c) {      // c = et < 64
-      const int hh = c >> 5, cc = c & 31;
-      return (S.wsum[hh * 4][cc] + S.wsum[hh * 4 + 1][cc]) + (S.wsum[hh * 4 + 2][cc] + S.wsum[hh * 4 + 3][cc]);
+      const int hh = c >> 5, ch = c & 31;
+      return (S.wsum[hh * 4][ch] + S.wsum[hh * 4 + 1][ch]) + (S.wsum[hh * 4 + 2][ch] + S.wsum[hh * 4 + 3][ch]);
     };
-    // 64 per-CTA sums -> every CTA of the cluster gets all of them; returns the sample total in S.ca_tot
+    // 64 per-CTA sums -> every CTA of the cluster gets all of them; the sample total lands in S.ca_tot
     auto all_gather = [&]() {
       const uint32_t par = ca_count & 1u, ph = (ca_count >> 1) & 1u;
       if (et < 64) {
@@ -425,24 +544,13 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
       ptx::named_bar_sync(1, kEpi);
     };
 
-    // L2 prefetch of the HBM-cold operands (saved forward activations) of op `i`
-    auto prefetch_op = [&](const int i) {
-      if (i >= p.n_ops || h != 0) return;
-      const COp& nx = p.ops[i];
-      const uint8_t* src = (nx.flags & SRB_MASK) ? nx.e : ((nx.flags & SRB_CHAIN_CA_BWD_FUSED) ? nx.e2 : nullptr);
-      if (!src) return;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) prefetch_l2(src + goff0 + (size_t)j * 1024u);
-    };
-    prefetch_op(0);
-
     for (int op = 0; op < p.n_ops; ++op) {
       const COp& o = p.ops[op];
       const uint32_t flags = o.flags;
       const int ob = (op + 1) & 1;
       const int bsel = op & 1;
+      const int res_mode = o.res_mode;
       if (et < 64) S.bias[bsel][et] = o.bias ? __ldg(o.bias + et) : 0.f;
-      prefetch_op(op + 1);
       ptx::named_bar_sync(1, kEpi);
       const float* bias_h = &S.bias[bsel][h * 32];
       const float scale = o.scale;
@@ -454,7 +562,7 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
       auto load_acc = [&](const int q, float (&v)[32], const bool release) {
         const uint32_t g = (uint32_t)(3 * op + q), slot = g & 3u;
         uint32_t acc[32];
-        ptx::tmem_ld_32x32b_x32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + slot * 64u + (uint32_t)(h * 32), acc);
+        ptx::tmem_ld_32x32b_x32(tmem_acc + tm_lane + slot * 64u + (uint32_t)(h * 32), acc);
         ptx::tmem_ld_wait();
         if (release) {
           ptx::tc_fence_before();
@@ -476,6 +584,26 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
           v[i] += bq.x; v[i + 1] += bq.y; v[i + 2] += bq.z; v[i + 3] += bq.w;
         }
       };
+      // residual operand of position q (tile j) by the op's mode
+      auto fetch_residual = [&](uint4 (&ev)[4], const int q, const int j) {
+        if (res_mode == RES_INPLACE) {
+          load_centre(ev, j, ob);
+        } else if (res_mode == RES_TMEM) {
+          uint32_t r16[16];
+          tmem_ld_x16(park_addr(op & 1, q), r16);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) ev[g] = make_uint4(r16[g * 4], r16[g * 4 + 1], r16[g * 4 + 2], r16[g * 4 + 3]);
+        } else {
+          const uint8_t* src = o.e + goff0 + (size_t)j * 1024u;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) ev[g] = ldg128(src + g * 16);
+        }
+      };
+      auto park = [&](const uint32_t (&pk)[16], const int q) {
+        tmem_st_x16(park_addr(op & 1, q), pk);
+        tmem_st_wait();
+      };
 
       if (!(flags & (SRB_CHAIN_CA | SRB_CHAIN_CA_BWD_FUSED))) {
         // ---------------- plain conv: bias, ReLU, scale, mask or residual (arithmetic = conv_chain.cu) ----------------
@@ -483,12 +611,9 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
           constexpr uint32_t FK = decltype(FC)::value;
           const uint32_t F = (FK == kGeneric) ? ((flags & 15u) | kScaled) : FK;     // compile-time constant unless generic
           const int j = mirror ? 2 - q : q;
-          const size_t goff = goff0 + (size_t)j * 1024u;
           uint4 ev[4];
-          if (F & (SRB_MASK | SRB_RESIDUAL)) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) ev[g] = ldg128(o.e + goff + g * 16);
-          }
+          if (F & SRB_MASK) take_operand(ev);
+          if (F & SRB_RESIDUAL) fetch_residual(ev, q, j);
           wait_acc(q);
           if (et == 0) CL_TRACE(op, q == 0 ? 4 : (q == 1 ? 9 : 11));
           float v[32];
@@ -504,34 +629,22 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
             for (int i = 0; i < 32; ++i) v[i] *= scale;
           }
           if (F & SRB_MASK) {
+            float fm[32];
+            unpack4(ev, fm);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint32_t mw[4] = {ev[g].x, ev[g].y, ev[g].z, ev[g].w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 fm = unpack_bf16x2(mw[e]);
-                if (!(fm.x > 0.f)) v[g * 8 + e * 2] = 0.f;
-                if (!(fm.y > 0.f)) v[g * 8 + e * 2 + 1] = 0.f;
-              }
-            }
+            for (int i = 0; i < 32; ++i)
+              if (!(fm[i] > 0.f)) v[i] = 0.f;
           }
           if (F & SRB_RESIDUAL) {
+            float fr[32];
+            unpack4(ev, fr);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint32_t mw[4] = {ev[g].x, ev[g].y, ev[g].z, ev[g].w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 fm = unpack_bf16x2(mw[e]);
-                v[g * 8 + e * 2] += fm.x;
-                v[g * 8 + e * 2 + 1] += fm.y;
-              }
-            }
+            for (int i = 0; i < 32; ++i) v[i] += fr[i];
           }
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) stg128(o.y + goff + g * 16, make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]));
+          if (o.park) park(pk, q);
           store_x(pk, j, q, ob);
           if (F & SRB_COLSUM) {          // sums of the STORED (bf16-rounded) values, as the other conv kernels
 #pragma unroll
@@ -543,7 +656,7 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
           }
           if (et == 0 && q == 0) CL_TRACE(op, 6);
           publish(q, ob, op);
-          if (et == 0) CL_TRACE(op, q == 0 ? 8 : (q == 1 ? 10 : 12));
+          copy_out_x(o.y, j, ob);
         };
         auto run = [&](auto FC) {
 #pragma unroll 1
@@ -570,11 +683,11 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
       } else if (flags & SRB_CHAIN_CA) {
         // ---------------- RCAB conv2 + CALayer + skip (rcan.py:10-29,54) ----------------
         const int Cr = o.ca_cr;
-        // pass 1: t = conv + bias (bf16) -> global; pooled sums of the stored values; accumulators stay in TMEM
+        const bool fast = Cr <= 4;
+        // pass 1: t = conv + bias (bf16) -> staging tile -> global; pooled sums of the stored values; accumulators stay in TMEM
 #pragma unroll 1
         for (int q = 0; q < 3; ++q) {
           const int j = mirror ? 2 - q : q;
-          const size_t goff = goff0 + (size_t)j * 1024u;
           wait_acc(q);
           if (et == 0) CL_TRACE(op, q == 0 ? 4 : (q == 1 ? 9 : 11));
           float v[32];
@@ -590,24 +703,24 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
               rs[g * 8 + e * 2] += fr.x;
               rs[g * 8 + e * 2 + 1] += fr.y;
             }
-            stg128(o.y + goff + g * 16, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+            ptx::sts128(el + (((uint32_t)(h * 4 + g) ^ (uint32_t)tx) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
           }
+          ptx::named_bar_sync(1, kEpi);
+          copy_out_e(o.y, j);
+          ptx::named_bar_sync(1, kEpi);          // staging tile free for the next position
         }
         // gate operands do not depend on the pool: fetch them while the sums travel
-        float w1a[2] = {0.f, 0.f}, w1b[2] = {0.f, 0.f}, b1v[2] = {0.f, 0.f};
-        {
-          int u = 0;
-          for (int jj = w8; jj < Cr && u < 2; jj += 8, ++u) {
-            w1a[u] = __ldg(o.ca_w1 + jj * 64 + lane);
-            w1b[u] = __ldg(o.ca_w1 + jj * 64 + lane + 32);
-            b1v[u] = __ldg(o.ca_b1 + jj);
-          }
+        float w1a = 0.f, w1b = 0.f, b1v = 0.f;
+        if (fast && w8 < Cr) {
+          w1a = __ldg(o.ca_w1 + w8 * 64 + lane);
+          w1b = __ldg(o.ca_w1 + w8 * 64 + lane + 32);
+          b1v = __ldg(o.ca_b1 + w8);
         }
-        float w2r[kMaxCr], b2v = 0.f;
+        float w2r[4] = {0.f, 0.f, 0.f, 0.f}, b2v = 0.f;
         if (et < 64) {
           b2v = __ldg(o.ca_b2 + et);
-#pragma unroll
-          for (int jj = 0; jj < kMaxCr; ++jj) w2r[jj] = jj < Cr ? __ldg(o.ca_w2 + et * Cr + jj) : 0.f;
+          if (fast)
+            for (int jj = 0; jj < Cr; ++jj) w2r[jj] = __ldg(o.ca_w2 + et * Cr + jj);
         }
         reduce_cta(rs);
         all_gather();
@@ -621,34 +734,33 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
           }
         }
         ptx::named_bar_sync(1, kEpi);
-        {
-          int u = 0;
-          for (int jj = w8; jj < Cr; jj += 8, ++u) {
-            float a = w1a[u] * S.ca_s[lane] + w1b[u] * S.ca_s[lane + 32];
-            a = warp_sum(a);
-            if (lane == 0) S.ca_z[jj] = fmaxf(a + b1v[u], 0.f);
+        if (fast) {
+          if (w8 < Cr) {
+            const float a = warp_sum(w1a * S.ca_s[lane] + w1b * S.ca_s[lane + 32]);
+            if (lane == 0) S.ca_z[w8] = fmaxf(a + b1v, 0.f);
+          }
+        } else {
+          for (int jj = w8; jj < Cr; jj += 8) {
+            const float a = warp_sum(__ldg(o.ca_w1 + jj * 64 + lane) * S.ca_s[lane] + __ldg(o.ca_w1 + jj * 64 + lane + 32) * S.ca_s[lane + 32]);
+            if (lane == 0) S.ca_z[jj] = fmaxf(a + __ldg(o.ca_b1 + jj), 0.f);
           }
         }
         ptx::named_bar_sync(1, kEpi);
         if (et < 64) {
           float u = b2v;
-#pragma unroll
-          for (int jj = 0; jj < kMaxCr; ++jj)
-            if (jj < Cr) u += w2r[jj] * S.ca_z[jj];
+          for (int jj = 0; jj < Cr; ++jj) u += (fast ? w2r[jj & 3] : __ldg(o.ca_w2 + et * Cr + jj)) * S.ca_z[jj];
           const float yv = 1.f / (1.f + expf(-u));
           S.ca_y[et] = yv;
           if (rank == 0) o.ca_y[(size_t)n * 64 + et] = yv;
         }
         ptx::named_bar_sync(1, kEpi);
-        // pass 2: out = t * gate + skip -> global, X[ob] and the neighbours' halos
+        // pass 2: out = t * gate + skip -> X[ob] (+ the neighbours' halos) -> global
         const float* yh = &S.ca_y[h * 32];
 #pragma unroll 1
         for (int q = 0; q < 3; ++q) {
           const int j = mirror ? 2 - q : q;
-          const size_t goff = goff0 + (size_t)j * 1024u;
           uint4 ev[4];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) ev[g] = ldg128(o.e + goff + g * 16);
+          fetch_residual(ev, q, j);
           float v[32];
           load_acc(q, v, true);
           add_bias(v);
@@ -664,27 +776,23 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
               pk[g * 4 + e] = pack_bf16x2(fmaf(ft.x, yh[ch], fx.x), fmaf(ft.y, yh[ch + 1], fx.y));
             }
           }
-#pragma unroll
-          for (int g = 0; g < 4; ++g) stg128(o.y2 + goff + g * 16, make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]));
+          if (o.park) park(pk, q);
           store_x(pk, j, q, ob);
           publish(q, ob, op);
-          if (et == 0) CL_TRACE(op, q == 0 ? 8 : (q == 1 ? 10 : 12));
+          copy_out_x(o.y2, j, ob);
         }
       } else {
         // ---------------- dgrad conv (+ residual) fused with the CALayer backward of the block whose dL/dout it produces --------
         const int Cr = o.ca_cr;
+        const bool fast = Cr <= 4;
         const bool has_res = (flags & SRB_RESIDUAL) != 0;
-        // pass 1: g = conv (* scale) + residual (bf16) -> global and X[ob] centre (scratch); running sums of g * t
+        // pass 1: g = conv (* scale) + residual (bf16) -> X[ob] centre (scratch) -> global; running sums of g * t
 #pragma unroll 1
         for (int q = 0; q < 3; ++q) {
           const int j = mirror ? 2 - q : q;
-          const size_t goff = goff0 + (size_t)j * 1024u;
           uint4 ev[4], tv[4];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            ev[g] = has_res ? ldg128(o.e + goff + g * 16) : make_uint4(0, 0, 0, 0);
-            tv[g] = ldg128(o.e2 + goff + g * 16);
-          }
+          take_operand(tv);
+          if (has_res) fetch_residual(ev, q, j);
           wait_acc(q);
           if (et == 0) CL_TRACE(op, q == 0 ? 4 : (q == 1 ? 9 : 11));
           float v[32];
@@ -694,54 +802,65 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] *= scale;
           }
-          const uint32_t off = (uint32_t)j * 1024u + (uint32_t)ob * kXStride;
+          if (has_res) {
+            float fr[32];
+            unpack4(ev, fr);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint32_t rw[4] = {ev[g].x, ev[g].y, ev[g].z, ev[g].w}, tw[4] = {tv[g].x, tv[g].y, tv[g].z, tv[g].w};
-            uint32_t pk[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 fr = unpack_bf16x2(rw[e]);
-              pk[e] = pack_bf16x2(v[g * 8 + e * 2] + fr.x, v[g * 8 + e * 2 + 1] + fr.y);
-              const float2 fg = unpack_bf16x2(pk[e]), ft = unpack_bf16x2(tw[e]);
-              rs[g * 8 + e * 2] = fmaf(fg.x, ft.x, rs[g * 8 + e * 2]);
-              rs[g * 8 + e * 2 + 1] = fmaf(fg.y, ft.y, rs[g * 8 + e * 2 + 1]);
-            }
-            const uint4 pv = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            stg128(o.y + goff + g * 16, pv);
-            ptx::sts128(xl + off + (((uint32_t)(h * 4 + g) ^ sw_l) << 4), pv);
+            for (int i = 0; i < 32; ++i) v[i] += fr[i];
           }
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          {
+            float ft[32];
+            unpack4(tv, ft);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 fg = unpack_bf16x2(pk[i]);
+              rs[2 * i] = fmaf(fg.x, ft[2 * i], rs[2 * i]);
+              rs[2 * i + 1] = fmaf(fg.y, ft[2 * i + 1], rs[2 * i + 1]);
+            }
+          }
+          if (o.park) park(pk, q);
+          store_centre(pk, j, ob);
+          ptx::named_bar_sync(1, kEpi);
+          copy_out_x(o.y, j, ob);
         }
         // everything the gate backward needs that does not depend on the sample sums
-        float w1a[2] = {0.f, 0.f}, w1b[2] = {0.f, 0.f}, b1v[2] = {0.f, 0.f}, w2a[2] = {0.f, 0.f}, w2b[2] = {0.f, 0.f};
-        {
-          int u = 0;
-          for (int jj = w8; jj < Cr && u < 2; jj += 8, ++u) {
-            w1a[u] = __ldg(o.ca_w1 + jj * 64 + lane);
-            w1b[u] = __ldg(o.ca_w1 + jj * 64 + lane + 32);
-            b1v[u] = __ldg(o.ca_b1 + jj);
-            w2a[u] = __ldg(o.ca_w2 + lane * Cr + jj);
-            w2b[u] = __ldg(o.ca_w2 + (lane + 32) * Cr + jj);
-          }
+        float w1a = 0.f, w1b = 0.f, b1v = 0.f, w2a = 0.f, w2b = 0.f;
+        if (fast && w8 < Cr) {
+          w1a = __ldg(o.ca_w1 + w8 * 64 + lane);
+          w1b = __ldg(o.ca_w1 + w8 * 64 + lane + 32);
+          b1v = __ldg(o.ca_b1 + w8);
+          w2a = __ldg(o.ca_w2 + lane * Cr + w8);
+          w2b = __ldg(o.ca_w2 + (lane + 32) * Cr + w8);
         }
-        float w2r[kMaxCr], w1c[kMaxCr], b2v = 0.f;
+        float w2r[4] = {0.f, 0.f, 0.f, 0.f}, w1c[4] = {0.f, 0.f, 0.f, 0.f}, b2v = 0.f;
         if (et < 64) {
           b2v = __ldg(o.ca_b2 + et);
-#pragma unroll
-          for (int jj = 0; jj < kMaxCr; ++jj) {
-            w2r[jj] = jj < Cr ? __ldg(o.ca_w2 + et * Cr + jj) : 0.f;
-            w1c[jj] = jj < Cr ? __ldg(o.ca_w1 + jj * 64 + et) : 0.f;
-          }
+          if (fast)
+            for (int jj = 0; jj < Cr; ++jj) {
+              w2r[jj] = __ldg(o.ca_w2 + et * Cr + jj);
+              w1c[jj] = __ldg(o.ca_w1 + jj * 64 + et);
+            }
           S.ca_s[et] = o.ca_s[(size_t)n * 64 + et];      // written by the forward launch
           S.ca_y[et] = o.ca_y[(size_t)n * 64 + et];
         }
         reduce_cta(rs);                                   // (barrier: ca_s / ca_y visible)
-        {
-          int u = 0;
-          for (int jj = w8; jj < Cr; jj += 8, ++u) {
-            float a = warp_sum(w1a[u] * S.ca_s[lane] + w1b[u] * S.ca_s[lane + 32]);
+        if (fast) {
+          if (w8 < Cr) {
+            float a = warp_sum(w1a * S.ca_s[lane] + w1b * S.ca_s[lane + 32]);
             if (lane == 0) {
-              a += b1v[u];
+              a += b1v;
+              S.ca_z[w8] = fmaxf(a, 0.f);
+              S.ca_dv[w8] = a > 0.f ? 1.f : 0.f;
+            }
+          }
+        } else {
+          for (int jj = w8; jj < Cr; jj += 8) {
+            float a = warp_sum(__ldg(o.ca_w1 + jj * 64 + lane) * S.ca_s[lane] + __ldg(o.ca_w1 + jj * 64 + lane + 32) * S.ca_s[lane + 32]);
+            if (lane == 0) {
+              a += __ldg(o.ca_b1 + jj);
               S.ca_z[jj] = fmaxf(a, 0.f);
               S.ca_dv[jj] = a > 0.f ? 1.f : 0.f;
             }
@@ -751,26 +870,26 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
         if (et == 0) CL_TRACE(op, 14);
         if (et < 64) {
           float u = b2v;
-#pragma unroll
-          for (int jj = 0; jj < kMaxCr; ++jj)
-            if (jj < Cr) u += w2r[jj] * S.ca_z[jj];
+          for (int jj = 0; jj < Cr; ++jj) u += (fast ? w2r[jj & 3] : __ldg(o.ca_w2 + et * Cr + jj)) * S.ca_z[jj];
           const float sp = 1.f / (1.f + expf(-u)), sn = 1.f / (1.f + expf(u));
           S.ca_du[et] = S.ca_tot[et] * (sp * sn);         // sigmoid'(u) from u itself
         }
         ptx::named_bar_sync(1, kEpi);
-        {
-          int u = 0;
-          for (int jj = w8; jj < Cr; jj += 8, ++u) {
-            const float dz = warp_sum(w2a[u] * S.ca_du[lane] + w2b[u] * S.ca_du[lane + 32]);
+        if (fast) {
+          if (w8 < Cr) {
+            const float dz = warp_sum(w2a * S.ca_du[lane] + w2b * S.ca_du[lane + 32]);
+            if (lane == 0) S.ca_dv[w8] *= dz;
+          }
+        } else {
+          for (int jj = w8; jj < Cr; jj += 8) {
+            const float dz = warp_sum(__ldg(o.ca_w2 + lane * Cr + jj) * S.ca_du[lane] + __ldg(o.ca_w2 + (lane + 32) * Cr + jj) * S.ca_du[lane + 32]);
             if (lane == 0) S.ca_dv[jj] *= dz;
           }
         }
         ptx::named_bar_sync(1, kEpi);
         if (et < 64) {
           float d = 0.f;
-#pragma unroll
-          for (int jj = 0; jj < kMaxCr; ++jj)
-            if (jj < Cr) d += w1c[jj] * S.ca_dv[jj];
+          for (int jj = 0; jj < Cr; ++jj) d += (fast ? w1c[jj & 3] : __ldg(o.ca_w1 + jj * 64 + et)) * S.ca_dv[jj];
           S.ca_ds[et] = d * inv_hw;
         }
         if (rank == 0) {                                  // parameter gradients, once per sample
@@ -782,7 +901,7 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
           if (et < Cr) atomicAdd(o.ca_db1 + et, S.ca_dv[et]);
         }
         ptx::named_bar_sync(1, kEpi);
-        // pass 2: dt = g * gate + ds / HW, in place in X[ob] (+ halos) and to global; column sums of dt
+        // pass 2: dt = g * gate + ds / HW, in place in X[ob] (+ halos) -> global; column sums of dt
         const float* yh = &S.ca_y[h * 32];
         const float* dsh = &S.ca_ds[h * 32];
 #pragma unroll
@@ -790,13 +909,12 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
 #pragma unroll 1
         for (int q = 0; q < 3; ++q) {
           const int j = mirror ? 2 - q : q;
-          const size_t goff = goff0 + (size_t)j * 1024u;
-          const uint32_t off = (uint32_t)j * 1024u + (uint32_t)ob * kXStride;
+          uint4 gv[4];
+          load_centre(gv, j, ob);
           uint32_t pk[16];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const uint4 gv = ptx::lds128(xl + off + (((uint32_t)(h * 4 + g) ^ sw_l) << 4));
-            const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+            const uint32_t gw[4] = {gv[g].x, gv[g].y, gv[g].z, gv[g].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 fg = unpack_bf16x2(gw[e]);
@@ -807,11 +925,9 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
               rs[ch + 1] += fd.y;
             }
           }
-#pragma unroll
-          for (int g = 0; g < 4; ++g) stg128(o.y2 + goff + g * 16, make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]));
           store_x(pk, j, q, ob);
           publish(q, ob, op);
-          if (et == 0) CL_TRACE(op, q == 0 ? 8 : (q == 1 ? 10 : 12));
+          copy_out_x(o.y2, j, ob);
         }
         if (o.colsum2) {
           reduce_cta(rs);
@@ -840,17 +956,35 @@ bool cluster_enabled() {
   return !(e && e[0] == '0');
 }
 
+int encode_5d(srb_ctx* ctx, CUtensorMap* map, void* ptr, int slots, int N, int H, int W, int box_w, int box_h) {
+  cuuint64_t dims[5] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)slots};
+  cuuint64_t strides[4] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128, (cuuint64_t)N * H * W * 128};
+  cuuint32_t box[5] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled);
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    srb_set_error("srb_conv_chain: cuTensorMapEncodeTiled failed with CUresult %d (slots=%d N=%d H=%d W=%d box %dx%d)", (int)r, slots, N, H,
+                  W, box_w, box_h);
+    return 4;
+  }
+  return 0;
+}
+
 }  // namespace
 
 // The cluster form takes a chain when: H % 16 == 0, W in {24, 48}, (H/16) * (W/24) <= 8 CTAs per sample; every op is a
-// conv whose input is the previous op's result (y, or y2 for the two-phase CALayer ops); no standalone CA_BWD tile op.
-// Returns 1 if it can run the chain, 0 if not (srb_conv_chain then uses the L2-flag kernel).
+// conv whose input is the previous op's result (y, or y2 for the two-phase CALayer ops); no standalone CA_BWD tile op;
+// CALayer-forward ops (which use the operand-tile buffer as staging) and TMA operand tiles (MASK / CA_BWD_FUSED) do not
+// occur in the same chain.  Returns 1 if it can run the chain, 0 if not (srb_conv_chain then uses the L2-flag kernel).
 int srb_chain_cluster_eligible(const srb_chain_desc* d) {
   if (!cluster_enabled()) return 0;
   if (d->H % 16 != 0 || (d->W != 24 && d->W != 48) || d->H < 16) return 0;
   const int bands = d->H / 16, halves = d->W / 24;
   if (bands * halves > kMaxCluster) return 0;
   uint16_t prev = SRB_CHAIN_NONE;
+  bool any_ca = false, any_tile = false;
   for (int i = 0; i < d->n_ops; ++i) {
     const srb_chain_op& o = d->ops[i];
     if (o.kind != SRB_CHAIN_CONV) return 0;
@@ -858,24 +992,29 @@ int srb_chain_cluster_eligible(const srb_chain_desc* d) {
     const uint32_t fl = o.flags;
     if (fl & ~(uint32_t)(SRB_RELU | SRB_RESIDUAL | SRB_MASK | SRB_COLSUM | SRB_CHAIN_CA | SRB_CHAIN_CA_BWD_FUSED)) return 0;
     if ((fl & SRB_MASK) && (fl & SRB_RESIDUAL)) return 0;
+    if (fl & SRB_MASK) any_tile = true;
     if (fl & SRB_CHAIN_CA) {
       if ((fl & (SRB_RELU | SRB_MASK | SRB_CHAIN_CA_BWD_FUSED)) || !(fl & SRB_RESIDUAL) || o.scale != 1.f) return 0;
       if (o.ca_cr < 1 || o.ca_cr > kMaxCr) return 0;
+      any_ca = true;
       prev = o.y2;
     } else if (fl & SRB_CHAIN_CA_BWD_FUSED) {
       if (fl & (SRB_RELU | SRB_MASK | SRB_COLSUM)) return 0;
       if (o.ca_cr < 1 || o.ca_cr > kMaxCr) return 0;
+      any_tile = true;
       prev = o.y2;
     } else {
       prev = o.y;
     }
   }
+  if (any_ca && any_tile) return 0;
   return 1;
 }
 
 int srb_chain_cluster_launch(srb_ctx* ctx, const srb_chain_desc* d, void* stream) {
   static_assert(sizeof(CParams) + sizeof(CMaps) < 32000, "kernel parameters exceed the 32 KB limit");
   static_assert(kSmemBytes <= 227u * 1024u, "shared memory budget");
+  static_assert(kParkBase + 2 * kParkArea <= kTmemCols, "TMEM budget");
   CParams* pp = new CParams();
   CMaps* mm = new CMaps();
   struct Guard {
@@ -895,6 +1034,7 @@ int srb_chain_cluster_launch(srb_ctx* ctx, const srb_chain_desc* d, void* stream
   p.n_ops = d->n_ops;
   p.trace = reinterpret_cast<long long*>(d->trace);
   const size_t slot_bytes = (size_t)d->N * d->H * d->W * 128u;
+  bool used[4] = {false, false, false, false};
   auto slot_ptr = [&](uint16_t r, const char* what, int op, uint8_t** out) -> int {
     *out = nullptr;
     if (r == SRB_CHAIN_NONE) return 0;
@@ -926,7 +1066,9 @@ int srb_chain_cluster_launch(srb_ctx* ctx, const srb_chain_desc* d, void* stream
     if ((rc = slot_ptr(o.y2, "y2", i, &y2))) return rc;
     if ((rc = slot_ptr(o.e, "mask/residual", i, &e))) return rc;
     if ((rc = slot_ptr(o.e2, "saved t", i, &e2))) return rc;
-    c.y = y; c.y2 = y2; c.e = e; c.e2 = e2;
+    c.y = y; c.y2 = y2; c.e = e;
+    c.park = 0;
+    c.pad = 0;
     SRB_REQUIRE(y != nullptr, "srb_conv_chain: op %d needs a y buffer", i);
     const bool m = (o.flags & SRB_MASK) != 0, r = (o.flags & SRB_RESIDUAL) != 0;
     SRB_REQUIRE(!(m || r) || e != nullptr, "srb_conv_chain: op %d needs a mask/residual buffer", i);
@@ -943,6 +1085,22 @@ int srb_chain_cluster_launch(srb_ctx* ctx, const srb_chain_desc* d, void* stream
       SRB_REQUIRE(o.ca_w1 && o.ca_b1 && o.ca_w2 && o.ca_b2 && o.ca_s && o.ca_y && o.ca_dw1 && o.ca_db1 && o.ca_dw2 && o.ca_db2 && y2 && e2,
                   "srb_conv_chain: op %d: CA_BWD_FUSED pointers missing", i);
     }
+    // operand tile by TMA
+    c.t_ref = m ? o.e : ((o.flags & SRB_CHAIN_CA_BWD_FUSED) ? o.e2 : (uint16_t)SRB_CHAIN_NONE);
+    if (c.t_ref != SRB_CHAIN_NONE) used[c.t_ref >> 14] = true;
+    // where the residual comes from: still in X[out] (it was the previous op's input), parked in TMEM by the op before
+    // the previous one, or global memory (read by the thread that owns the pixel)
+    c.res_mode = RES_NONE;
+    if (r) {
+      if (i >= 1 && o.e == d->ops[i - 1].x) {
+        c.res_mode = RES_INPLACE;
+      } else if (i >= 2 && o.e == d->ops[i - 2].y && !(d->ops[i - 2].flags & SRB_CHAIN_CA)) {
+        c.res_mode = RES_TMEM;
+        p.ops[i - 2].park = 1;
+      } else {
+        c.res_mode = RES_GLOBAL;
+      }
+    }
   }
   SRB_REQUIRE(d->weights && d->n_layers > 0, "srb_conv_chain: conv ops need a filter bank");
   EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled);
@@ -953,14 +1111,17 @@ int srb_chain_cluster_launch(srb_ctx* ctx, const srb_chain_desc* d, void* stream
     SRB_REQUIRE(d->space_base[sp] != nullptr && slot < d->space_slots[sp], "srb_conv_chain: op 0 x reference outside the declared spaces");
     SRB_REQUIRE(((uintptr_t)d->space_base[sp] & 127) == 0, "srb_conv_chain: space %d must be 128-byte aligned", sp);
     p.x0_slot = slot;
-    cuuint64_t dims[5] = {64, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N, (cuuint64_t)d->space_slots[sp]};
-    cuuint64_t strides[4] = {128, (cuuint64_t)d->W * 128, (cuuint64_t)d->H * d->W * 128, (cuuint64_t)d->N * d->H * d->W * 128};
-    cuuint32_t box[5] = {64, (cuuint32_t)kXW, (cuuint32_t)kXH, 1, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult cr = fn(&mm->x0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, d->space_base[sp], dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SRB_REQUIRE(cr == CUDA_SUCCESS, "srb_conv_chain: cuTensorMapEncodeTiled(input window) failed with CUresult %d", (int)cr);
+    int rc = encode_5d(ctx, &mm->x0, d->space_base[sp], d->space_slots[sp], d->N, d->H, d->W, kXW, kXH);
+    if (rc) return rc;
+  }
+  for (int s = 0; s < 4; ++s) {
+    if (!used[s]) {
+      mm->tile[s] = mm->x0;      // never dereferenced; keeps the parameter block initialised
+      continue;
+    }
+    SRB_REQUIRE(((uintptr_t)d->space_base[s] & 127) == 0, "srb_conv_chain: space %d must be 128-byte aligned", s);
+    int rc = encode_5d(ctx, &mm->tile[s], d->space_base[s], d->space_slots[s], d->N, d->H, d->W, 8, 16);
+    if (rc) return rc;
   }
   {
     SRB_REQUIRE(((uintptr_t)d->weights & 127) == 0, "srb_conv_chain: filter bank must be 128-byte aligned");

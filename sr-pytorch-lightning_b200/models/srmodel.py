@@ -96,6 +96,18 @@ def _lazy(pkg: str, attr: str):
     return make
 
 
+class _LazyObject:
+    """Callable built from `factory()` on first call."""
+
+    def __init__(self, factory):
+        self._factory, self._obj = factory, None
+
+    def __call__(self, *a, **k):
+        if self._obj is None:
+            self._obj = self._factory()
+        return self._obj(*a, **k)
+
+
 def psnr(sr: torch.Tensor, hr: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
     """piq.psnr(data_range=1, reduction='mean') restatement (reference srmodel.py:52)."""
     mse = ((sr.float() - hr.float()) ** 2).flatten(1).mean(1)
@@ -128,25 +140,48 @@ def ssim(sr: torch.Tensor, hr: torch.Tensor, k1=0.01, k2=0.03, sigma=1.5, size=1
 _supported_losses = {
     'adaptive': _lazy('robust_loss_pytorch', 'AdaptiveImageLossFunction'),
     'dists': _lazy('piq', 'DISTS'),
+    'edge_loss': _lazy('losses', 'EdgeLoss'),
+    'flip': _lazy('losses', 'FLIPLoss'),
     'haarpsi': _lazy('piq', 'HaarPSILoss'),
     'l1': _L1,
     'l2': nn.MSELoss,
     'lpips': _lazy('piq', 'LPIPS'),
     'mae': _L1,
     'mse': nn.MSELoss,
+    'pencil_sketch': _lazy('losses', 'PencilSketchLoss'),
     'pieapp': _lazy('piq', 'PieAPP'),
 }
 
 _supported_metrics = {
     'BRISQUE': _lazy('piq', 'brisque'),
+    'FLIP': _lazy('losses', 'FLIP'),
     'LPIPS': _lazy('piq', 'LPIPS'),
     'MS-SSIM': _lazy('piq', 'multi_scale_ssim'),
     'PSNR': psnr,
     'SSIM': ssim,
 }
 
+def _lazy_optimizer(name: str):
+    class _Missing:
+        __name__ = name
+
+        def __new__(cls, *a, **k):
+            import importlib
+            try:
+                mod = importlib.import_module('torch_optimizer')
+            except Exception as e:  # noqa: BLE001
+                raise RuntimeError(f"optimizer '{name}' needs the optional package 'torch_optimizer': {e}") from e
+            return getattr(mod, name)(*a, **k)
+    return _Missing
+
+
+# same names as the reference registry (srmodel.py:30-66); entries whose package (piq / kornia-based `losses` /
+# torch_optimizer / robust_loss_pytorch) is not installed are registered lazily and raise only when USED
 _supported_optimizers = {
     'ADAM': optim.Adam,
+    'Ranger': _lazy_optimizer('Ranger'),
+    'RangerVA': _lazy_optimizer('RangerVA'),
+    'RangerQH': _lazy_optimizer('RangerQH'),
     'RMSprop': optim.RMSprop,
     'SGD': optim.SGD,
 }
@@ -305,7 +340,10 @@ class SRModel(_Base, ABC):
             if metric not in _supported_metrics:
                 raise AttributeError(f'Couldn\'t find metric {metric}. Supported metrics: '
                                      f'{", ".join(_supported_metrics)}')
-            used.append((metric, _supported_metrics[metric]() if metric in {'LPIPS'} else _supported_metrics[metric]))
+            fn = _supported_metrics[metric]
+            if metric in {'LPIPS', 'FLIP'}:      # metric objects (reference srmodel.py:507-509): built on first use, so a
+                fn = _LazyObject(fn)             # missing optional package fails when the metric is computed, not at construction
+            used.append((metric, fn))
         return used
 
     def _calculate_losses(self, img_sr: torch.Tensor, img_hr: torch.Tensor) -> dict[str, torch.Tensor]:
@@ -347,6 +385,9 @@ class SRModel(_Base, ABC):
             raise ValueError(f'Optimizer not recognized: {optimizer}. Supported optimizers: '
                              f'{", ".join(_supported_optimizers)}')
         params = {}
+        if optimizer_params:
+            self._logger.warning('optimizer_params=%s are applied here; the reference shadows this argument '
+                                 '(srmodel.py:602) and always trains with the optimizer defaults', optimizer_params)
         for item in optimizer_params:
             name, value = item.strip().split('=')
             name = name.strip()

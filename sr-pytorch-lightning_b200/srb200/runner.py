@@ -29,6 +29,15 @@ class Runner:
         self.model = model
         self.scale = int(scale if scale is not None else model._scale_factor)
         self.lr_shape = tuple(lr_shape)
+        # optimizer hyper-parameters the model was configured with (SRModel._parse_optimizer_config) win over the defaults
+        op = dict(getattr(model, "_optim_params", None) or {})
+        unknown = set(op) - {"lr", "betas", "eps", "weight_decay"}
+        if unknown:
+            raise NotImplementedError(f"optimizer_params {sorted(unknown)} are not supported by the fused Adam step")
+        lr = float(op.get("lr", lr))
+        betas = tuple(op.get("betas", betas))
+        eps = float(op.get("eps", eps))
+        weight_decay = float(op.get("weight_decay", weight_decay))
         self.step_runner = TrainStep(model, self.lr_shape, self.scale, lr=lr, betas=betas, eps=eps,
                                      weight_decay=weight_decay, use_graph=use_graph, process_group=process_group)
         self._captured = False
@@ -99,7 +108,10 @@ class Runner:
     # ---- evaluation ---------------------------------------------------------------------------
     def _refresh_packed(self):
         """The captured step re-packs the bf16 / K-major weight copies BEFORE its forward, so after a step
-        they are one Adam update behind the fp32 parameters: re-pack once before evaluating."""
+        they are one Adam update behind the fp32 parameters: re-pack once before evaluating.  Packed copies that
+        are not in the table (first used by an evaluation on another shape) are invalidated and re-pack lazily."""
+        from . import ops
+        ops.invalidate_packed()
         if self.step_runner.pack_table is not None:
             self.step_runner.pack_table.run()
 
@@ -142,6 +154,8 @@ class Runner:
             flat.v.copy_(st["adam_v"])
             flat.step_dev.fill_(int(st["adam_step"]))
         self.global_step = int(st.get("global_step", 0))
+        from . import ops
+        ops.invalidate_packed()
 
     def close(self):
         self.step_runner.close()

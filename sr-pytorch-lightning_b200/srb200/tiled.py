@@ -172,6 +172,8 @@ class TiledEDSR:
         bufs = [torch.empty((1, mine.shape[1], (r1 - r0) * s, mine.shape[3]), dtype=mine.dtype, device=mine.device)
                 for r0, r1 in parts]
         dist.all_gather(bufs, mine, group=self.ex.group) if len({b.shape for b in bufs}) == 1 else \
-            [dist.broadcast(bufs[i] if i != self.ex.rank else mine, src=i, group=self.ex.group) for i in range(self.ex.parts)]
+            [dist.broadcast(bufs[i] if i != self.ex.rank else mine,
+                            src=dist.get_global_rank(self.ex.group, i) if self.ex.group is not None else i, group=self.ex.group)
+             for i in range(self.ex.parts)]
         bufs[self.ex.rank] = mine
         return torch.cat(bufs, dim=2)

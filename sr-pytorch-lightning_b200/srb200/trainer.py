@@ -69,6 +69,20 @@ class FlatParams:
                 del p._srb_grad_live
 
 
+def check_supported(model):
+    """The fused step implements exactly what the reference's default configuration trains with: ONE unit-weight L1
+    loss (`losses: l1`, srmodel.py:37,549) and Adam (srmodel.py:57,145-154).  Anything else must fail loudly instead
+    of silently training as L1/Adam; such configurations can still use `SRModel.training_step` with a torch optimizer."""
+    losses = getattr(model, "_losses", None)
+    if losses is not None:
+        if len(losses) != 1 or losses[0].name not in ("l1", "mae") or float(losses[0].weight) != 1.0:
+            desc = "+".join(f"{l.weight}*{l.name}" for l in losses)
+            raise NotImplementedError(f"TrainStep fuses a single unit-weight L1 loss; the model was built with losses='{desc}'")
+    opt = getattr(model, "_optim", None)
+    if opt is not None and opt is not torch.optim.Adam:
+        raise NotImplementedError(f"TrainStep fuses Adam; the model was built with optimizer {opt.__name__}")
+
+
 class TrainStep:
     """One training step of an SRModel subclass on fixed-shape batches.
 
@@ -77,6 +91,7 @@ class TrainStep:
 
     def __init__(self, model, lr_shape, scale: int, *, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, use_graph: bool = True, process_group=None):
+        check_supported(model)
         self.model = model
         self.flat = FlatParams(model)
         dev = self.flat.flat.device
@@ -93,6 +108,15 @@ class TrainStep:
         self.launches_per_step = 0
         self.arena = ops.ZeroArena(dev)
         self.pack_table = None
+        self.sync_from_rank0()
+
+    def sync_from_rank0(self):
+        """Replicas start from rank 0's parameters and Adam state, as Lightning DDP broadcasts them for the reference
+        (call again after loading a checkpoint on one rank only)."""
+        if self.world > 1:
+            src = dist.get_global_rank(self.pg, 0) if self.pg is not None else 0
+            for t in (self.flat.flat, self.flat.m, self.flat.v, self.flat.step_dev):
+                dist.broadcast(t, src=src, group=self.pg)
 
     # the work of one step; captured once
     def _body(self):
