@@ -276,6 +276,35 @@ int  srb_adam_step(srb_ctx*, float* param, const float* grad, float* m, float* v
                    const int32_t* step_dev, float grad_scale, void* stream);
 int  srb_inc_counter(srb_ctx*, int32_t* counter, void* stream);
 
+/* ---- spatial tiling of large-image inference (BASELINE.json configs[4]; the reference runs the whole frame through
+ * SRModel.predict_step on one device, models/srmodel.py:375-380) -----------------------------------------------------
+ * Each rank owns a row strip; a layer's output is [1, t + rows + t, W, C] with t halo rows on either side.  One launch per
+ * layer copies this rank's first / last t owned rows into the neighbours' halo rows through NVLink peer memory, stores the
+ * frame number into the neighbours' flag slot (release, system scope) and waits for the neighbours' flags (acquire), so
+ * the next conv on the stream reads complete halos; capturable in a CUDA graph.  Before pushing, the ranks shake hands
+ * ("my buffer of this layer is complete, you may write its halo rows": the conv before this call wrote them too).
+ * Peer pointers come from srb_ipc_open. */
+typedef struct srb_halo_desc {
+  const void* src_top;      /* first t owned rows of this rank's buffer            */
+  const void* src_bot;      /* last t owned rows                                   */
+  void*       dst_up;       /* upper neighbour's bottom halo rows (peer) or NULL   */
+  void*       dst_dn;       /* lower neighbour's top halo rows (peer) or NULL      */
+  int64_t     slab_bytes;   /* t * W * Cs * elem_size, multiple of 16              */
+  int64_t*    flag_up;      /* upper neighbour's "from below" slot pair {ready, data} of this layer (peer) or NULL */
+  int64_t*    flag_dn;      /* lower neighbour's "from above" pair (peer) or NULL  */
+  const int64_t* wait_up;   /* own "from above" pair (the upper neighbour writes it) or NULL */
+  const int64_t* wait_dn;   /* own "from below" pair or NULL                       */
+  const int64_t* frame;     /* device counter: current frame number, >= 1 (bump it with srb_inc_counter64 once per frame) */
+  uint32_t*   done;         /* zero-initialised device word (CTA completion counter, self-resetting) */
+} srb_halo_desc;
+int  srb_halo_exchange(srb_ctx*, const srb_halo_desc*, void* stream);
+int  srb_inc_counter64(srb_ctx*, int64_t* counter, void* stream);
+/* device memory other processes on this node can map (cudaMalloc + cudaIpcGetMemHandle; zero-filled) */
+int  srb_ipc_alloc(srb_ctx*, size_t bytes, void** ptr, unsigned char handle[64]);
+int  srb_ipc_open(srb_ctx*, const unsigned char handle[64], void** ptr);
+int  srb_ipc_close(srb_ctx*, void* ptr);
+int  srb_ipc_free(srb_ctx*, void* ptr);
+
 /* ---- diagnostics (not on the product path) -------------------------------------------------
  * tcgen05.mma throughput probe: `blocks` CTAs each issue `iters` MMAs 128 x N x 16 (bf16, SS,
  * 128-B swizzle; mn_major selects the operand major-ness) and write their elapsed SM cycles. */

@@ -47,6 +47,9 @@ def report(tr, n_ops, ctas, label, kinds=None):
     nxt = t[:, 1:, 0]
     print(f"  {'q1 published -> NEXT op rdy0':40s} {(nxt[:, mid] - t[:, :-1, :][:, mid, 10]).mean():8.0f} ns")
     print(f"  {'q2 published -> NEXT op rdy1':40s} {(t[:, 1:, 2][:, mid] - t[:, :-1, :][:, mid, 12]).mean():8.0f} ns")
+    w = t[:, mid, 16:24] - t[:, mid, 9:10]
+    print("  q1: acc1 -> tile-barrier arrive per epilogue warp (ns): " + " ".join(f"{x:.0f}" for x in w.mean(axis=(0, 1))))
+    print(f"  q1: last warp arrive -> publisher released {(t[:, mid, 24] - t[:, mid, 16:24].max(axis=2)).mean():.0f} ns;  released -> arrives issued (lane 0) {(t[:, mid, 10] - t[:, mid, 24]).mean():.0f} ns, (lane 1) {(t[:, mid, 25] - t[:, mid, 24]).mean():.0f} ns")
     c = ctas // 2
     for op in range(n_ops // 2, n_ops // 2 + 2):
         base = t[c, op, 0]
@@ -62,7 +65,7 @@ def run_long(n=16, depth=24):
     bank = ops.FilterBank().get(list(zip(ws, packs)), L.PACK_FWD)
     A = torch.zeros((depth, n, h, w, 64), dtype=bf, device=DEV)
     ctas = n * 6
-    trace = torch.zeros(ctas * depth * 16 + 4096, dtype=torch.int64, device=DEV)
+    trace = torch.zeros(ctas * depth * 32 + 4096, dtype=torch.int64, device=DEV)
 
     def build():
         ch = ops.Chain(n, h, w, x.device)
@@ -87,7 +90,7 @@ def run_long(n=16, depth=24):
     trace.zero_()
     ch.run(bank, trace=trace)
     torch.cuda.synchronize()
-    tr = trace[:ctas * depth * 16].cpu().numpy().reshape(ctas, depth, 16)
+    tr = trace[:ctas * depth * 32].cpu().numpy().reshape(ctas, depth, 32)
     report(tr, depth, ctas, "24 dependent relu convs on [16,48,48,64]")
 
 
@@ -109,7 +112,7 @@ def run_group():
             q.items.clear()
     torch.cuda.synchronize()
     for direction in ("forward", "backward"):
-        trace = torch.zeros(ctas * n_ops * 16 + 65536, dtype=torch.int64, device=DEV)
+        trace = torch.zeros(ctas * n_ops * 32 + 65536, dtype=torch.int64, device=DEV)
         if direction == "forward":
             ops.CHAIN_TRACE = trace
             with torch.no_grad():
@@ -123,7 +126,7 @@ def run_group():
                 q.items.clear()
             ops.CHAIN_TRACE = None
         torch.cuda.synchronize()
-        tr = trace[:ctas * n_ops * 16].cpu().numpy().reshape(ctas, n_ops, 16)
+        tr = trace[:ctas * n_ops * 32].cpu().numpy().reshape(ctas, n_ops, 32)
         if direction == "forward":
             kinds = ["conv1" if i % 2 == 0 else "conv2+CA" for i in range(40)] + ["tail"]
         else:

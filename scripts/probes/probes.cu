@@ -674,6 +674,141 @@ static void run_p8(int num_sms) {
   CK(cudaFree(dcy));
 }
 
+// ------------------------------------------------------------------------------------------------
+// P9: does a K-major SWIZZLE_128B A operand whose 8-row groups do NOT start on a 1024-byte swizzle atom (the row-shifted
+//     window taps of the 3x3 convs: start = (kh * pitch + kw) * 128 B, stride between 8-row groups = pitch * 128 B) cost
+//     tensor throughput?  128 x 64 x 16 MMAs back to back, A start offset / group stride varied, B fixed.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) p9_kernel(int a_off_bytes, int a_sbo_bytes, int iters, int vary, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  for (int i = threadIdx.x; i < (160 * 1024) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem_raw + (base - ptx::smem_u32(smem_raw)))[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (threadIdx.x < 32) {
+    ptx::tmem_alloc(&slot, 256);
+    ptx::tmem_relinquish();
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = slot;
+  if (threadIdx.x == 0) {
+    constexpr uint32_t idesc = ptx::idesc_bf16_f32(128, 64, 0, 0);
+    const uint32_t a_lo = ptx::smem_desc_lo(base + (uint32_t)a_off_bytes, 16u);
+    const uint32_t b_lo = ptx::smem_desc_lo(base + 128 * 1024, 16u);
+    const uint32_t hi_a = ptx::smem_desc_hi_sw128((uint32_t)a_sbo_bytes);
+    constexpr uint32_t hi_b = ptx::smem_desc_hi_sw128(1024u);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)      // vary: walk the four 32-byte k-steps and three row shifts like a conv tap loop
+        ptx::umma_bf16_lohi(tmem, a_lo + (vary ? (uint32_t)(u * 2 + ((i >> 2) % 3) * 8) : 0u), hi_a, b_lo + (vary ? (uint32_t)(u * 2) : 0u), hi_b,
+                            idesc, 1u);
+    }
+    ptx::umma_commit(&bar);
+    ptx::mbar_wait(&bar, 0);
+    out[blockIdx.x] = clock64() - t0;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 256);
+  }
+}
+
+static void run_p9(int num_sms) {
+  long long* dcy;
+  CK(cudaMalloc(&dcy, 256 * 8));
+  const int smem = 162 * 1024;
+  CK(cudaFuncSetAttribute(p9_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int iters = 4096;
+  struct Case { int off, sbo, vary; const char* what; };
+  const Case cases[] = {
+      {0, 1024, 0, "aligned start, groups 1024 B apart (dense tile)"},
+      {128, 1024, 0, "start +128 B, groups 1024 B apart"},
+      {0, 1280, 0, "aligned start, groups 1280 B apart (pitch 10)"},
+      {128, 1280, 0, "start +128 B, pitch 10"},
+      {0, 3328, 0, "aligned start, groups 3328 B apart (pitch 26)"},
+      {128, 3328, 0, "start +128 B, pitch 26"},
+      {3328 + 256, 3328, 0, "start (1 row + 2 px), pitch 26"},
+      {0, 3328, 1, "pitch 26, k-steps and kw shifts walked as in the conv"},
+      {0, 1280, 1, "pitch 10, k-steps and kw shifts walked as in the conv"},
+      {0, 1024, 1, "dense tile, k-steps walked"},
+  };
+  for (const Case& c : cases) {
+    CK(cudaMemset(dcy, 0, 256 * 8));
+    p9_kernel<<<num_sms, 128, smem>>>(c.off, c.sbo, iters, c.vary, dcy);
+    CK(cudaDeviceSynchronize());
+    std::vector<long long> cy(num_sms);
+    CK(cudaMemcpy(cy.data(), dcy, num_sms * 8, cudaMemcpyDeviceToHost));
+    double mean = 0;
+    for (auto v : cy) mean += (double)v / num_sms;
+    printf("P9 %-62s: %6.1f cyc/MMA (128x64x16)\n", c.what, mean / iters);
+  }
+  CK(cudaFree(dcy));
+}
+
+// ------------------------------------------------------------------------------------------------
+// P10: is the 128-byte swizzle of a TMA tensor STORE a function of the absolute shared-memory address (as it is for UMMA
+//      operands, P1) or of the offset inside the box?  A buffer of 128-byte pixel rows is written with the absolute-address
+//      swizzle (16-byte chunk c of row r sits at r * 128 + ((c ^ (r & 7)) << 4)); one box of 8 rows is stored to global from
+//      a source that starts `row0` rows into the buffer (not 1024-byte aligned unless row0 % 8 == 0).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) p10_kernel(const __grid_constant__ CUtensorMap tm, int row0, int* bad_out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* bp = smem_raw + (base - ptx::smem_u32(smem_raw));
+  // logical value of (row r, 16-bit element e): r * 64 + e, as bf16 bit patterns are irrelevant -> use raw uint16
+  for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {      // 64 rows x 8 chunks
+    const int r = i >> 3, c = i & 7;
+    uint16_t v[8];
+    for (int k = 0; k < 8; ++k) v[k] = (uint16_t)(r * 64 + c * 8 + k);
+    *reinterpret_cast<uint4*>(bp + r * 128 + ((c ^ (r & 7)) << 4)) = *reinterpret_cast<uint4*>(v);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&tm)),
+                 "r"(base + (uint32_t)row0 * 128u), "r"(0), "r"(0)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  (void)bad_out;
+}
+
+static void run_p10() {
+  uint16_t* dout;
+  CK(cudaMalloc(&dout, 8 * 64 * 2));
+  CK(cudaFuncSetAttribute(p10_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024));
+  for (int row0 : {0, 8, 1, 3, 27, 29}) {
+    CK(cudaMemset(dout, 0xFF, 8 * 64 * 2));
+    CUtensorMap tm;
+    cuuint64_t dims[2] = {64, 8};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, 8};
+    make_map(&tm, dout, 2, dims, strides, box);
+    p10_kernel<<<1, 128, 16 * 1024>>>(tm, row0, nullptr);
+    CK(cudaDeviceSynchronize());
+    std::vector<uint16_t> h(8 * 64);
+    CK(cudaMemcpy(h.data(), dout, 8 * 64 * 2, cudaMemcpyDeviceToHost));
+    int bad = 0;
+    for (int r = 0; r < 8; ++r)
+      for (int e = 0; e < 64; ++e) bad += h[r * 64 + e] != (uint16_t)((row0 + r) * 64 + e);
+    printf("P10 TMA store of 8 rows from a source %2d rows (= %4d B) into an absolute-address-swizzled buffer: %d / 512 elements wrong%s\n", row0,
+           row0 * 128, bad, bad == 0 ? "  -> swizzle follows the absolute address" : "");
+  }
+  CK(cudaFree(dout));
+}
+
 int main(int argc, char** argv) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
@@ -695,5 +830,7 @@ int main(int argc, char** argv) {
   if (want("p3")) run_p3(prop.multiProcessorCount);
   if (want("p7")) run_p7();
   if (want("p8")) run_p8(prop.multiProcessorCount);
+  if (want("p9")) run_p9(prop.multiProcessorCount);
+  if (want("p10")) run_p10();
   return 0;
 }

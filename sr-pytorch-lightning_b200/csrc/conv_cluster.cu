@@ -36,6 +36,8 @@ namespace {
 
 constexpr int kThreads = 384;                       // 12 warps: operand tiles, MMA, filters, spare, 8 x epilogue
 constexpr int kEpi = 256;
+constexpr int kPub = kEpi + 32;                     // epilogue threads + the publisher warp
+constexpr int kBarTile = 2, kBarPair = 6;           // named barriers: 2 + q per tile position (publisher); 6 + quarter (warp pairs)
 constexpr int kXW = 26, kXH = 18;                   // activation buffer: 24 + 2 columns, 16 + 2 rows
 constexpr uint32_t kXBytes = kXH * kXW * 128u;      // 59904
 constexpr uint32_t kXStride = 60u * 1024u;
@@ -67,28 +69,30 @@ struct COp {
   uint16_t t_ref;        // operand tile by TMA: ReLU mask (MASK) or saved t (CA_BWD_FUSED); SRB_CHAIN_NONE if none
   uint8_t res_mode;      // RES_*
   uint8_t park;          // keep the packed result y in TMEM for the op after next (its residual)
-  uint32_t pad;
+  uint16_t y_ref, y2_ref;   // (space << 14) | slot of y / y2 for the TMA row stores
 };
 
 struct CParams {
   int N, H, W, bands, halves, n_ops, x0_slot;
-  long long* trace;      // diagnostics: [grid][n_ops][16] globaltimer ns (CL_TRACE)
+  long long* trace;      // diagnostics: [grid][n_ops][32] globaltimer ns (CL_TRACE)
   COp ops[SRB_CHAIN_MAX_OPS];
 };
 
-// diagnostics: trace[(cta * n_ops + op) * 16 + event] = globaltimer (ns)
+// diagnostics: trace[(cta * n_ops + op) * 32 + event] = globaltimer (ns)
+//  16-23: epilogue warp w arrives on the tile barrier of q1; 24: publisher released by it; 25: publisher's arrives issued
 //  MMA thread: 0 position-0 window ready, 1 position-0 MMAs issued, 2 position-1 window ready, 3 all MMAs issued
 //  epilogue thread 0: 4 acc(q0) full, 5 q0 loaded from TMEM, 6 q0 stores issued, 7 q0 proxy fence done, 8 q0 published,
 //                     9 acc(q1) full, 10 q1 published, 11 acc(q2) full, 12 q2 published, 13 op complete, 14 sums gathered
 #define CL_TRACE(op, ev)                                                                                      \
   do {                                                                                                        \
-    if (p.trace) p.trace[((size_t)blockIdx.x * p.n_ops + (op)) * 16 + (ev)] = (long long)ptx::globaltimer_ns(); \
+    if (p.trace) p.trace[((size_t)blockIdx.x * p.n_ops + (op)) * 32 + (ev)] = (long long)ptx::globaltimer_ns(); \
   } while (0)
 
 struct CMaps {
   CUtensorMap x0;        // 5-D (c, w, h, n, slot) over the space of op 0's input, box 64 x 26 x 18
   CUtensorMap w;         // 4-D (cin, cout, tap, layer), box 64 x 64 x 3
   CUtensorMap tile[4];   // per space: box 64 x 8 x 16 (operand tiles)
+  CUtensorMap row[4];    // per space: box 64 x 8 x 1 (one tile row: X[out] -> global)
 };
 
 struct Small {
@@ -123,6 +127,18 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t raddr, uint4 v) {
 }
 __device__ __forceinline__ void st_cluster_f32(uint32_t raddr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory");
+}
+// Remote store that carries its own completion: the bytes are counted on an mbarrier of the DESTINATION CTA when they have
+// landed (complete_tx, release at cluster scope).  The consumer's barrier expects the byte count of a phase, so no thread
+// here has to run a cluster-scope release fence after its halo stores (that fence — MEMBAR + ERRBAR + CGAERRBAR — waited
+// for the CTA's in-flight global / TMA stores too and cost ~0.85 us per tile, profiles/r02_cluster_trace_v5.txt).
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, uint4 v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w), "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_b32(uint32_t raddr, uint32_t v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr), "r"(v), "r"(rbar) : "memory");
 }
 // release at cluster scope: cumulative over everything ordered before it in this CTA (the arriving thread has been
 // through a bar.sync with the writers) — the cluster-scope form of conv_chain.cu's red.release.gpu after a barrier
@@ -163,6 +179,10 @@ __device__ __forceinline__ void fence_writer() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #endif
 }
+// producer side of a named barrier: does not wait (the publisher warp is the only bar.sync participant)
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ uint4 ldg128(const uint8_t* p) {      // plain (coherent) 16-byte global load
   uint4 v;
   asm volatile("ld.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
@@ -177,6 +197,13 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, 
       "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
 }
 
 // 32 lanes x 16 consecutive 32-bit columns: thread i of the warp owns lane (base_lane + i)
@@ -289,13 +316,12 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
     ptx::mbar_init(&S.x_full, 1);
     ptx::mbar_init(&S.e_full, 1);
     ptx::mbar_init(&S.e_empty, 8);
-    const uint32_t nv = (has_up ? 1u : 0u) + (has_dn ? 1u : 0u);
-    const uint32_t ca = 2u + 2u * nv + (has_side ? 1u + nv : 0u);
-    const uint32_t cb = 3u + 3u * nv;
+    // ready[buffer][A]: this CTA's positions 0 and 1 (two local arrivals) + the neighbours' halo bytes of their positions
+    // 0 and 1 (st.async complete_tx); ready[buffer][B]: position 2 (one local arrival) + the neighbours' position-2 halo bytes
     for (int b = 0; b < 2; ++b) {
-      ptx::mbar_init(&S.ready[b][0], ca);
-      ptx::mbar_init(&S.ready[b][1], cb);
-      ptx::mbar_init(&S.pool_full[b], (uint32_t)csize);
+      ptx::mbar_init(&S.ready[b][0], 2);
+      ptx::mbar_init(&S.ready[b][1], 1);
+      ptx::mbar_init(&S.pool_full[b], 1);
     }
     ptx::fence_mbar_init();
   }
@@ -375,6 +401,27 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
         }
       }
     }
+  } else if (warp == 3) {
+    // ===================== publisher =====================
+    // The epilogue warps only ARRIVE on a named barrier once a tile sits in X[out]; this warp waits for it and arrives on this
+    // CTA's own ready barrier, so that no epilogue warp ever blocks on a tile barrier.
+    // Local arrivals only (CTA scope): the neighbours' halo bytes are counted by the st.async stores themselves.
+    const uint32_t nv = (has_up ? 1u : 0u) + (has_dn ? 1u : 0u);
+    const uint32_t ra_bytes = nv * 2048u + (has_side ? 2048u + nv * 128u : 0u);      // rows of positions 0-1, side column, corners
+    const uint32_t rb_bytes = nv * 1024u;                                            // rows of position 2
+    for (int op = 0; op < p.n_ops; ++op) {
+      const int ob = (op + 1) & 1;
+      for (int q = 0; q < 3; ++q) {
+        ptx::named_bar_sync(kBarTile + q, kPub);
+        if (lane == 0) {
+          if (q == 1) CL_TRACE(op, 24);
+          if (q == 0) ptx::mbar_arrive_expect_tx(&S.ready[ob][0], ra_bytes);
+          else if (q == 1) ptx::mbar_arrive(&S.ready[ob][0]);
+          else ptx::mbar_arrive_expect_tx(&S.ready[ob][1], rb_bytes);
+          CL_TRACE(op, q == 0 ? 8 : (q == 1 ? 10 : 12));
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ===================== epilogue: 8 warps, thread = (pixel of the tile, 32-channel half) =====================
     const int et = (int)threadIdx.x - 128;          // 0..255
@@ -388,30 +435,38 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
     const uint32_t idx_l = (uint32_t)((ty + 1) * kXW + tx + 1);
     const uint32_t xl = xbase + idx_l * 128u, sw_l = idx_l & 7u;
     const uint32_t el = ebase + (uint32_t)row * 128u;            // this pixel's row of the operand tile (swizzle = tx)
+    // remote halo targets (buffer 0) and the destination CTA's ready barrier A of buffer 0 (buffer 1: + 16, barrier B: + 8)
     uint32_t up_a = 0, dn_a = 0, side_a = 0, dgu_a = 0, dgd_a = 0, sw_up = 0, sw_dn = 0, sw_side = 0, sw_dg = 0;
+    uint32_t up_b = 0, dn_b = 0, side_b = 0, dgu_b = 0, dgd_b = 0;
+    const uint32_t rdy0 = ptx::smem_u32(&S.ready[0][0]);
     if (has_up && ty == 0) {
       const uint32_t idx = (uint32_t)(17 * kXW + tx + 1);
       up_a = mapa(xbase + idx * 128u, (uint32_t)up_rank);
+      up_b = mapa(rdy0, (uint32_t)up_rank);
       sw_up = idx & 7u;
     }
     if (has_dn && ty == 15) {
       const uint32_t idx = (uint32_t)(tx + 1);
       dn_a = mapa(xbase + idx * 128u, (uint32_t)dn_rank);
+      dn_b = mapa(rdy0, (uint32_t)dn_rank);
       sw_dn = idx & 7u;
     }
     if (has_side && tx == (f == 0 ? 7 : 0)) {      // only used at position 0 (the tile next to the other half)
       const uint32_t col = f == 0 ? 0u : 25u;
       const uint32_t idx = (uint32_t)((ty + 1) * kXW) + col;
       side_a = mapa(xbase + idx * 128u, (uint32_t)side_rank);
+      side_b = mapa(rdy0, (uint32_t)side_rank);
       sw_side = idx & 7u;
       if (has_up && ty == 0) {
         const uint32_t di = (uint32_t)(17 * kXW) + col;
         dgu_a = mapa(xbase + di * 128u, (uint32_t)(up_rank + 1 - 2 * f));
+        dgu_b = mapa(rdy0, (uint32_t)(up_rank + 1 - 2 * f));
         sw_dg = di & 7u;
       }
       if (has_dn && ty == 15) {
         const uint32_t di = col;
         dgd_a = mapa(xbase + di * 128u, (uint32_t)(dn_rank + 1 - 2 * f));
+        dgd_b = mapa(rdy0, (uint32_t)(dn_rank + 1 - 2 * f));
         sw_dg = di & 7u;
       }
     }
@@ -420,28 +475,9 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
     // cooperative tile copy (shared -> global): 8 consecutive threads move one pixel's 128-byte line; thread = (16-byte
     // chunk cc, pixel column ctx, pixel rows cty + 4k for k = 0..3).  (4 * 26) % 8 == 0, so the swizzle is the same for all k.
     const int cc = et & 7, ctx = (et >> 3) & 7, cty = et >> 6;
-    const uint32_t cidx = (uint32_t)((cty + 1) * kXW + ctx + 1);
-    const uint32_t cx = xbase + cidx * 128u + (((uint32_t)cc ^ (cidx & 7u)) << 4);          // + j * 1024 + ob * kXStride + k * 4 * 26 * 128
     const uint32_t ce = ebase + (uint32_t)(et >> 3) * 128u + (((uint32_t)cc ^ (uint32_t)ctx) << 4);   // + k * 32 * 128
     const size_t cg0 = ((((size_t)n * p.H + band * 16 + cty) * p.W) + f * 24 + ctx) * 128u + (size_t)cc * 16u;   // + j * 1024 + k * 4 * W * 128
     const size_t cg_k = (size_t)4 * p.W * 128u;
-    // "ready" arrivals: lanes 0-8 of the first epilogue warp own one target each (address for buffer 0; + 16 for buffer 1)
-    //   0 own A  1 own B  2 up A  3 up B  4 down A  5 down B  6 side A  7 up-diagonal A  8 down-diagonal A
-    uint32_t arr_a = 0, arr_qmask = 0;
-    if (w8 == 0 && lane < 9) {
-      const uint32_t ra = ptx::smem_u32(&S.ready[0][0]), rb = ptx::smem_u32(&S.ready[0][1]);
-      switch (lane) {
-        case 0: arr_a = mapa(ra, rank); arr_qmask = 3u; break;
-        case 1: arr_a = mapa(rb, rank); arr_qmask = 7u; break;
-        case 2: if (has_up) { arr_a = mapa(ra, up_rank); arr_qmask = 3u; } break;
-        case 3: if (has_up) { arr_a = mapa(rb, up_rank); arr_qmask = 7u; } break;
-        case 4: if (has_dn) { arr_a = mapa(ra, dn_rank); arr_qmask = 3u; } break;
-        case 5: if (has_dn) { arr_a = mapa(rb, dn_rank); arr_qmask = 7u; } break;
-        case 6: if (has_side) { arr_a = mapa(ra, side_rank); arr_qmask = 1u; } break;
-        case 7: if (has_side && has_up) { arr_a = mapa(ra, up_rank + 1 - 2 * f); arr_qmask = 1u; } break;
-        default: if (has_side && has_dn) { arr_a = mapa(ra, dn_rank + 1 - 2 * f); arr_qmask = 1u; } break;
-      }
-    }
     const uint32_t pool_bar0 = ptx::smem_u32(&S.pool_full[0]);
     uint32_t ca_count = 0;                          // two-phase (CALayer) ops so far
     uint32_t e_k = 0;                               // operand tiles consumed so far
@@ -449,18 +485,19 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
     // write this pixel's 32 channels into X[ob] (centre + the neighbours' halos)
     auto store_x = [&](const uint32_t (&pk)[16], const int j, const int q, const int ob) {
       const uint32_t off = (uint32_t)j * 1024u + (uint32_t)ob * kXStride;
+      const uint32_t boff = (uint32_t)ob * 16u + (q == 2 ? 8u : 0u);       // which ready barrier of the destination CTA
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const uint4 v = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
         const uint32_t c = (uint32_t)(h * 4 + g);
         ptx::sts128(xl + off + ((c ^ sw_l) << 4), v);
-        if (up_a) st_cluster_v4(up_a + off + ((c ^ sw_up) << 4), v);
-        if (dn_a) st_cluster_v4(dn_a + off + ((c ^ sw_dn) << 4), v);
+        if (up_a) st_async_v4(up_a + off + ((c ^ sw_up) << 4), v, up_b + boff);
+        if (dn_a) st_async_v4(dn_a + off + ((c ^ sw_dn) << 4), v, dn_b + boff);
         if (q == 0 && side_a) {
-          const uint32_t boff = (uint32_t)ob * kXStride;
-          st_cluster_v4(side_a + boff + ((c ^ sw_side) << 4), v);
-          if (dgu_a) st_cluster_v4(dgu_a + boff + ((c ^ sw_dg) << 4), v);
-          if (dgd_a) st_cluster_v4(dgd_a + boff + ((c ^ sw_dg) << 4), v);
+          const uint32_t xoff = (uint32_t)ob * kXStride;
+          st_async_v4(side_a + xoff + ((c ^ sw_side) << 4), v, side_b + boff);
+          if (dgu_a) st_async_v4(dgu_a + xoff + ((c ^ sw_dg) << 4), v, dgu_b + boff);
+          if (dgd_a) st_async_v4(dgd_a + xoff + ((c ^ sw_dg) << 4), v, dgd_b + boff);
         }
       }
     };
@@ -476,24 +513,31 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
 #pragma unroll
       for (int g = 0; g < 4; ++g) ev[g] = ptx::lds128(xl + off + (((uint32_t)(h * 4 + g) ^ sw_l) << 4));
     };
-    // all 256 threads have written position q of X[ob]: publish to the consumers' MMA issuers
-    auto publish = [&](const int q, const int ob, const int op) {
+    // this thread's part of position q is in X[ob] (and the neighbours' halos): hand it to the publisher warp
+    // (the publisher warp does the rest: release-arrive on the consumers' ready barriers)
+    auto publish = [&](const int q, const int op) {
       fence_writer();
+      named_bar_arrive(kBarTile + q, kPub);
       if (et == 0 && q == 0) CL_TRACE(op, 7);
-      ptx::named_bar_sync(1, kEpi);
-      if (arr_a && ((arr_qmask >> q) & 1u)) mbar_arrive_cluster(arr_a + (uint32_t)ob * 16u);
-      if (et == 0) CL_TRACE(op, q == 0 ? 8 : (q == 1 ? 10 : 12));
+      if (lane == 0 && q == 1) CL_TRACE(op, 16 + w8);
     };
-    // tile j of X[ob] -> global slot (after a barrier that follows the writes): full 128-byte lines per 8 lanes
-    auto copy_out_x = [&](uint8_t* slot, const int j, const int ob) {
-      const uint32_t s0 = cx + (uint32_t)j * 1024u + (uint32_t)ob * kXStride;
-      uint8_t* g0 = slot + cg0 + (size_t)j * 1024u;
-      uint4 v[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] = ptx::lds128(s0 + (uint32_t)k * (4u * kXW * 128u));
-#pragma unroll
-      for (int k = 0; k < 4; ++k) stg128(g0 + (size_t)k * cg_k, v[k]);
+    // Tile j of X[ob] -> global slot `ref`.  The two warps of a TMEM lane quarter hold the two channel halves of the same four
+    // tile rows: once both have written them (64-thread barrier) lanes 0-3 of the first issue one 1 KB TMA row store each.
+    // The rows start at 128-byte (not 1024-byte) aligned shared-memory addresses; the swizzle of a TMA store follows the
+    // absolute address just as the UMMA operand fetch does (profiles/r02_hw_probes_p10.txt).  Callers have run fence_writer().
+    auto store_rows = [&](const uint16_t ref, const int j, const int ob) {
+      // these rows of X[ob] are rewritten two ops (six tiles) later, by the two warps that meet here: before the partner
+      // may run on, the store issued five calls ago has finished reading shared memory
+      if (h == 0 && lane < 4) ptx::bulk_wait_group_read<4>();
+      ptx::named_bar_sync(kBarPair + quarter, 64);
+      if (h == 0 && lane < 4) {
+        const int trow = quarter * 4 + lane;
+        const uint32_t src = xbase + (uint32_t)ob * kXStride + (uint32_t)((trow + 1) * kXW + 1 + 8 * j) * 128u;
+        tma_store_5d(&maps.row[ref >> 14], src, 0, f * 24 + 8 * j, band * 16 + trow, n, ref & 0x3FFF);
+        ptx::bulk_commit_group();
+      }
     };
+    // staging tile -> global slot (after a barrier that follows the writes): full 128-byte lines per 8 lanes
     auto copy_out_e = [&](uint8_t* slot, const int j) {
       uint8_t* g0 = slot + cg0 + (size_t)j * 1024u;
       uint4 v[4];
@@ -507,6 +551,12 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
       ptx::mbar_wait(&S.e_full, e_k & 1u);
 #pragma unroll
       for (int g = 0; g < 4; ++g) tv[g] = ptx::lds128(el + (((uint32_t)(h * 4 + g) ^ (uint32_t)tx) << 4));
+      // The buffer is handed back for the next TMA load only once the loaded VALUES have arrived in registers (an
+      // instruction that consumes them cannot issue earlier): with the arrive issued right behind the loads, quarter-warp
+      // passes of an LDS.128 delayed in a busy shared-memory pipe were overtaken by the next tile's TMA write (torn masks
+      // at 8-lane granularity, profiles/r02_cluster_parity_v3_race.txt).
+      uint32_t dep = tv[0].x ^ tv[1].y ^ tv[2].z ^ tv[3].w;
+      asm volatile("mov.b32 %0, %0;" : "+r"(dep));
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&S.e_empty);
       ++e_k;
@@ -530,10 +580,9 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
       if (et < 64) {
         const float part = cta_total(et);
         const uint32_t slot = ptx::smem_u32(&S.pool[par][rank][et]);
-        for (int r = 0; r < csize; ++r) st_cluster_f32(mapa(slot, (uint32_t)r), part);
+        for (int r = 0; r < csize; ++r) st_async_b32(mapa(slot, (uint32_t)r), __float_as_uint(part), mapa(pool_bar0 + par * 8u, (uint32_t)r));
       }
-      ptx::named_bar_sync(1, kEpi);
-      if (w8 == 0 && lane < csize) mbar_arrive_cluster(mapa(pool_bar0 + par * 8u, (uint32_t)lane));
+      if (et == 64) ptx::mbar_arrive_expect_tx(&S.pool_full[par], (uint32_t)csize * 256u);     // 64 floats from every CTA of the cluster
       mbar_wait_cluster(&S.pool_full[par], ph);
       if (et < 64) {
         float t = 0.f;
@@ -655,8 +704,8 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
             }
           }
           if (et == 0 && q == 0) CL_TRACE(op, 6);
-          publish(q, ob, op);
-          copy_out_x(o.y, j, ob);
+          publish(q, op);
+          store_rows(o.y_ref, j, ob);
         };
         auto run = [&](auto FC) {
 #pragma unroll 1
@@ -778,8 +827,8 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
           }
           if (o.park) park(pk, q);
           store_x(pk, j, q, ob);
-          publish(q, ob, op);
-          copy_out_x(o.y2, j, ob);
+          publish(q, op);
+          store_rows(o.y2_ref, j, ob);
         }
       } else {
         // ---------------- dgrad conv (+ residual) fused with the CALayer backward of the block whose dL/dout it produces --------
@@ -823,8 +872,8 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
           }
           if (o.park) park(pk, q);
           store_centre(pk, j, ob);
-          ptx::named_bar_sync(1, kEpi);
-          copy_out_x(o.y, j, ob);
+          fence_writer();
+          store_rows(o.y_ref, j, ob);
         }
         // everything the gate backward needs that does not depend on the sample sums
         float w1a = 0.f, w1b = 0.f, b1v = 0.f, w2a = 0.f, w2b = 0.f;
@@ -900,6 +949,7 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
           if (et < 64) atomicAdd(o.ca_db2 + et, S.ca_du[et]);
           if (et < Cr) atomicAdd(o.ca_db1 + et, S.ca_dv[et]);
         }
+        if (h == 0 && lane < 4) ptx::bulk_wait_group_read<0>();      // dL/dout has left X[ob]: it may be rewritten in place
         ptx::named_bar_sync(1, kEpi);
         // pass 2: dt = g * gate + ds / HW, in place in X[ob] (+ halos) -> global; column sums of dt
         const float* yh = &S.ca_y[h * 32];
@@ -926,8 +976,8 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
             }
           }
           store_x(pk, j, q, ob);
-          publish(q, ob, op);
-          copy_out_x(o.y2, j, ob);
+          publish(q, op);
+          store_rows(o.y2_ref, j, ob);
         }
         if (o.colsum2) {
           reduce_cta(rs);
@@ -936,6 +986,7 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
       }
       if (et == 0) CL_TRACE(op, 13);
     }
+    if (h == 0 && lane < 4) ptx::bulk_wait_group<0>();      // all row stores complete before the CTA exits
   }
 
   ptx::tc_fence_before();
@@ -1034,7 +1085,7 @@ int srb_chain_cluster_launch(srb_ctx* ctx, const srb_chain_desc* d, void* stream
   p.n_ops = d->n_ops;
   p.trace = reinterpret_cast<long long*>(d->trace);
   const size_t slot_bytes = (size_t)d->N * d->H * d->W * 128u;
-  bool used[4] = {false, false, false, false};
+  bool used[4] = {false, false, false, false}, used_row[4] = {false, false, false, false};
   auto slot_ptr = [&](uint16_t r, const char* what, int op, uint8_t** out) -> int {
     *out = nullptr;
     if (r == SRB_CHAIN_NONE) return 0;
@@ -1068,7 +1119,10 @@ int srb_chain_cluster_launch(srb_ctx* ctx, const srb_chain_desc* d, void* stream
     if ((rc = slot_ptr(o.e2, "saved t", i, &e2))) return rc;
     c.y = y; c.y2 = y2; c.e = e;
     c.park = 0;
-    c.pad = 0;
+    c.y_ref = o.y;
+    c.y2_ref = o.y2;
+    used_row[o.y >> 14] = true;
+    if (o.y2 != SRB_CHAIN_NONE) used_row[o.y2 >> 14] = true;
     SRB_REQUIRE(y != nullptr, "srb_conv_chain: op %d needs a y buffer", i);
     const bool m = (o.flags & SRB_MASK) != 0, r = (o.flags & SRB_RESIDUAL) != 0;
     SRB_REQUIRE(!(m || r) || e != nullptr, "srb_conv_chain: op %d needs a mask/residual buffer", i);
@@ -1115,12 +1169,14 @@ int srb_chain_cluster_launch(srb_ctx* ctx, const srb_chain_desc* d, void* stream
     if (rc) return rc;
   }
   for (int s = 0; s < 4; ++s) {
-    if (!used[s]) {
-      mm->tile[s] = mm->x0;      // never dereferenced; keeps the parameter block initialised
-      continue;
-    }
+    mm->tile[s] = mm->x0;        // unused entries are never dereferenced; this keeps the parameter block initialised
+    mm->row[s] = mm->x0;
+    if (!used[s] && !used_row[s]) continue;
     SRB_REQUIRE(((uintptr_t)d->space_base[s] & 127) == 0, "srb_conv_chain: space %d must be 128-byte aligned", s);
-    int rc = encode_5d(ctx, &mm->tile[s], d->space_base[s], d->space_slots[s], d->N, d->H, d->W, 8, 16);
+    int rc = 0;
+    if (used[s]) rc = encode_5d(ctx, &mm->tile[s], d->space_base[s], d->space_slots[s], d->N, d->H, d->W, 8, 16);
+    if (rc) return rc;
+    if (used_row[s]) rc = encode_5d(ctx, &mm->row[s], d->space_base[s], d->space_slots[s], d->N, d->H, d->W, 8, 1);
     if (rc) return rc;
   }
   {

@@ -579,6 +579,15 @@ extern "C" int srb_inc_counter(srb_ctx* ctx, int32_t* counter, void* stream) {
   return 0;
 }
 
+__global__ void inc64_kernel(long long* c) { *c += 1; }
+
+extern "C" int srb_inc_counter64(srb_ctx* ctx, int64_t* counter, void* stream) {
+  SRB_REQUIRE(ctx && counter, "srb_inc_counter64: null argument");
+  inc64_kernel<<<1, 1, 0, S(stream)>>>(reinterpret_cast<long long*>(counter));
+  SRB_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int srb_adam_step(srb_ctx* ctx, float* param, const float* grad, float* m, float* v, int64_t n, float lr,
                              float beta1, float beta2, float eps, float weight_decay, int step,
                              const int32_t* step_dev, float grad_scale, void* stream) {

@@ -60,6 +60,11 @@ class ChainDesc(C.Structure):
                 ("counters", c_vp), ("trace", c_vp), ("tile_flags", c_vp)]
 
 
+class HaloDesc(C.Structure):
+    _fields_ = [("src_top", c_vp), ("src_bot", c_vp), ("dst_up", c_vp), ("dst_dn", c_vp), ("slab_bytes", c_i64),
+                ("flag_up", c_vp), ("flag_dn", c_vp), ("wait_up", c_vp), ("wait_dn", c_vp), ("frame", c_vp), ("done", c_vp)]
+
+
 class WgradItem(C.Structure):
     _fields_ = [("d", WgradDesc), ("x", c_vp), ("gy", c_vp), ("dw", c_vp), ("dbias", c_vp)]
 
@@ -97,6 +102,12 @@ PROTOTYPES = {
     "srb_l1_loss": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "srb_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_vp, c_f32, c_vp]),
     "srb_inc_counter": (c_i32, [c_vp, c_vp, c_vp]),
+    "srb_inc_counter64": (c_i32, [c_vp, c_vp, c_vp]),
+    "srb_halo_exchange": (c_i32, [c_vp, C.POINTER(HaloDesc), c_vp]),
+    "srb_ipc_alloc": (c_i32, [c_vp, C.c_size_t, C.POINTER(c_vp), C.c_char_p]),
+    "srb_ipc_open": (c_i32, [c_vp, C.c_char_p, C.POINTER(c_vp)]),
+    "srb_ipc_close": (c_i32, [c_vp, c_vp]),
+    "srb_ipc_free": (c_i32, [c_vp, c_vp]),
     "srb_probe_umma": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "srb_debug_set_trace": (c_i32, [c_vp, c_vp]),
 }

@@ -1,0 +1,179 @@
+"""Parity at the BASELINE.json sizes (GPU), against the CPU oracle run LIVE on the same seeded inputs (the golden
+fixtures are 16x16 / 24x24 images: these cases put the 96-CTA cluster chains, the 10-group arenas and the 400+-block
+weight-gradient planner through the same comparison).
+
+Bars (north_star): output relative L2 <= 1e-4 (fp32 mode) / 2e-2 (bf16 mode), also before add_mean; global relative
+L2 of all parameter gradients at the same bars; x4 PSNR within 0.01 dB of the oracle on natural images."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+RGB_MEAN = np.array((0.4488, 0.4371, 0.4040)).reshape(1, 3, 1, 1)
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def _trained_like(sd, seed=0, gain=1.0):
+    """Default-init weights are tiny past the first layers; rescale conv weights to variance-preserving magnitude
+    (what trained SR nets look like) so that the deep trunks carry signal: oracle/synth.py's recipe."""
+    from oracle.synth import synth_state_dict
+    shapes = {k: tuple(v.shape) for k, v in sd.items()}
+    frozen = {k: v.numpy() for k, v in sd.items() if k.startswith(("sub_mean", "add_mean"))}
+    out = synth_state_dict(shapes, seed=seed, gain=gain, frozen=frozen)
+    return {k: torch.from_numpy(v) for k, v in out.items()}
+
+
+def _fwd_bwd_case(cls, kw, okw, n, mode, gain):
+    import models
+    from oracle import sr_oracle
+    torch.manual_seed(0)
+    scale = kw.get("scale_factor", 4)
+    m = getattr(models, cls)(**kw)
+    sd = _trained_like({k: v.detach().clone() for k, v in m.state_dict().items()}, gain=gain)
+    m.load_state_dict(sd)
+    m.compute_dtype = mode
+    m = m.to(DEV)
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(n, 3, 48, 48, generator=g)
+    hr = torch.rand(n, 3, 48 * scale, 48 * scale, generator=torch.Generator().manual_seed(1))
+    out = m.training_step({"lr": x.to(DEV), "hr": hr.to(DEV)}, 0)
+    out["loss"].backward()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        sr = m.forward(x.to(DEV)).double().cpu().numpy()
+    # the oracle in fp32 on all host threads (fp64 would take minutes at this size; fp32-vs-fp64 oracle noise is 4e-7)
+    sr_ref, loss_ref, grads_ref = sr_oracle.forward_backward(cls, x, hr, {k: v.numpy() for k, v in sd.items()}, dtype=torch.float32, **okw)
+    sr_ref = sr_ref.double().numpy()
+    has_mean = cls in ("EDSR", "RCAN")
+    e_out = _rel(sr, sr_ref)
+    e_pre = _rel(sr - RGB_MEAN, sr_ref - RGB_MEAN) if has_mean else e_out
+    num = den = 0.0
+    worst = (0.0, "")
+    for k, p in m.named_parameters():
+        if not p.requires_grad:
+            continue
+        want = grads_ref[k].double().numpy()
+        d2 = float(((p.grad.double().cpu().numpy() - want) ** 2).sum())
+        w2 = float((want ** 2).sum())
+        num += d2
+        den += w2
+        worst = max(worst, ((d2 / max(w2, 1e-300)) ** 0.5, k))
+    e_grad = (num / den) ** 0.5
+    print(f"{cls} {mode} n={n}: out {e_out:.2e} pre-mean {e_pre:.2e} loss {out['loss'].item():.6f} vs {float(loss_ref):.6f} "
+          f"grad global {e_grad:.2e} worst tensor {worst[0]:.2e} ({worst[1]})")
+    tol = TOL[mode]
+    assert e_out < tol and e_pre < tol
+    assert abs(out["loss"].item() - float(loss_ref)) < tol * abs(float(loss_ref))
+    assert e_grad < tol
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_rcan_10x20_batch16_forward_and_all_gradients(mode):
+    """BASELINE.json configs[2] at its own size: RCAN 10 groups x 20 RCAB on 16 x 3x48x48, forward + L1 + every gradient."""
+    _fwd_bwd_case("RCAN", dict(n_feats=64, n_resblocks=20, n_resgroups=10, reduction=16, scale_factor=4),
+                  dict(n_resblocks=20, n_resgroups=10, scale=4), 16, mode, gain=0.7)
+
+
+def test_edsr_baseline_batch16_forward_and_all_gradients():
+    """BASELINE.json configs[1]."""
+    _fwd_bwd_case("EDSR", dict(n_feats=64, n_resblocks=16, res_scale=1.0, scale_factor=4),
+                  dict(n_resblocks=16, res_scale=1.0, scale=4), 16, "bf16", gain=0.6)
+
+
+def test_rdn_b_batch16_forward_and_all_gradients():
+    """BASELINE.json configs[3]: RDN-B on 16 x 48x48."""
+    _fwd_bwd_case("RDN", dict(rdn_config="B", scale_factor=4), dict(rdn_config="B", scale=4), 16, "bf16", gain=0.5)
+
+
+def test_edsr_large_32_blocks_forward():
+    """BASELINE.json configs[4] network (256 ch x 32 blocks, res_scale 0.1) on a 96x128 frame: conv_wide_kernel<128> end to end."""
+    import models
+    from oracle import sr_oracle
+    torch.manual_seed(0)
+    m = models.EDSR(n_feats=256, n_resblocks=32, res_scale=0.1, scale_factor=4)
+    sd = _trained_like({k: v.detach().clone() for k, v in m.state_dict().items()}, gain=1.0)
+    m.load_state_dict(sd)
+    m.compute_dtype = "bf16"
+    m = m.to(DEV)
+    x = torch.rand(1, 3, 96, 128, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        sr = m.forward(x.to(DEV)).double().cpu().numpy()
+        ref = sr_oracle.edsr_forward(x, sd, n_resblocks=32, res_scale=0.1, scale=4).double().numpy()
+    e_out, e_pre = _rel(sr, ref), _rel(sr - RGB_MEAN, ref - RGB_MEAN)
+    print(f"EDSR-large 96x128: out {e_out:.2e} pre-mean {e_pre:.2e}")
+    assert e_out < 2e-2 and e_pre < 2e-2
+
+
+def _natural_images():
+    """(name, HR tensor [1,3,424,640] in [0,1]) for sklearn's china.jpg / flower.jpg, centre-cropped."""
+    from sklearn.datasets import load_sample_image
+    out = []
+    for name in ("china.jpg", "flower.jpg"):
+        img = torch.from_numpy(load_sample_image(name).copy()).permute(2, 0, 1).float().div(255.0)   # 3 x 427 x 640
+        out.append((name, img[:, :424, :640].unsqueeze(0).contiguous()))
+    return out
+
+
+def _patch_batches(images, steps, batch=16, lr_size=48, scale=4, seed=0):
+    """Random HR crops of the natural images and their bicubic / 4 LR versions (srdata.py:57-80,228-229)."""
+    g = torch.Generator().manual_seed(seed)
+    hs = lr_size * scale
+    out = []
+    for _ in range(steps):
+        hrs = []
+        for _ in range(batch):
+            img = images[int(torch.randint(len(images), (1,), generator=g))][1]
+            y = int(torch.randint(img.shape[2] - hs + 1, (1,), generator=g))
+            x = int(torch.randint(img.shape[3] - hs + 1, (1,), generator=g))
+            hrs.append(img[:, :, y:y + hs, x:x + hs])
+        hr = torch.cat(hrs).contiguous()
+        lr = torch.nn.functional.interpolate(hr, size=(lr_size, lr_size), mode="bicubic", antialias=True, align_corners=False).clamp(0, 1)
+        out.append({"lr": lr.contiguous(), "hr": hr})
+    return out
+
+
+@pytest.mark.parametrize("cls,kw,okw", [
+    ("EDSR", dict(n_feats=64, n_resblocks=16, res_scale=1.0, scale_factor=4), dict(n_resblocks=16, res_scale=1.0, scale=4)),
+    ("RCAN", dict(n_feats=64, n_resblocks=4, n_resgroups=3, reduction=16, scale_factor=4), dict(n_resblocks=4, n_resgroups=3, scale=4)),
+])
+def test_psnr_parity_on_natural_images(cls, kw, okw):
+    """x4 PSNR of this repo's bf16 path vs the oracle (fp32 CPU) on identical TRAINED weights and natural images
+    (sklearn's china.jpg / flower.jpg); LR = bicubic / 4 as the reference builds it (srdata.py:228-229:
+    TF.resize(..., BICUBIC) = antialiased bicubic); validation_step semantics (clamp to [0,1], srmodel.py:224-225).
+    The weights come from a short training run of this repo's own step on patches of the two images (Runner.fit), so the
+    SR images are real reconstructions (PSNR in the 20s) and 0.01 dB is a real constraint on the bf16 error."""
+    import models
+    from oracle import sr_oracle
+    from srb200.runner import Runner
+    images = _natural_images()
+    torch.manual_seed(0)
+    m = getattr(models, cls)(**kw)
+    m.compute_dtype = "bf16"
+    m = m.to(DEV)
+    runner = Runner(m, (16, 3, 48, 48), 4, lr=2e-4)
+    losses = runner.fit(_patch_batches(images, 40), epochs=10)
+    print(f"{cls}: trained {len(losses)} steps, L1 {losses[0]:.4f} -> {losses[-1]:.4f}")
+    assert losses[-1] < 0.6 * losses[0]
+    runner._refresh_packed()
+    sd = {k: v.detach().float().cpu().clone() for k, v in m.state_dict().items()}
+    for name, hr in images:
+        lr = torch.nn.functional.interpolate(hr, size=(106, 160), mode="bicubic", antialias=True, align_corners=False).clamp(0, 1)
+        with torch.no_grad():
+            res = m.validation_step({"lr": lr.to(DEV), "hr": hr.to(DEV)}, 0)
+            key = [k for k in res if k.endswith("PSNR")][0]
+            psnr_ours = float(res[key])
+            ref = sr_oracle.FORWARDS[cls](lr, sd, **okw)
+            psnr_ref = float(sr_oracle.psnr(ref, hr))
+        print(f"{cls} {name}: PSNR ours {psnr_ours:.4f} dB, oracle {psnr_ref:.4f} dB, delta {psnr_ours - psnr_ref:+.4f}")
+        assert psnr_ref > 15.0
+        assert abs(psnr_ours - psnr_ref) <= 0.01
+    runner.close()

@@ -117,3 +117,24 @@ def test_oracle_matches_live_reference(name):
     for k, p in model.named_parameters():
         if p.requires_grad:
             assert rel_l2(grads[k].numpy(), p.grad.numpy()) < 1e-10, k
+
+
+@pytest.mark.parametrize("cls,kw,okw", [
+    ("EDSR", dict(n_feats=64, n_resblocks=16, scale_factor=4), dict(n_feats=64, n_resblocks=16, scale=4)),
+    ("EDSR", dict(n_feats=256, n_resblocks=3, scale_factor=3), dict(n_feats=256, n_resblocks=3, scale=3)),
+    ("EDSR", dict(n_feats=32, n_resblocks=2, scale_factor=8), dict(n_feats=32, n_resblocks=2, scale=8)),
+    ("RCAN", dict(n_resblocks=3, n_resgroups=2, scale_factor=4), dict(n_resblocks=3, n_resgroups=2, scale=4)),
+    ("RDN", dict(rdn_config="B", scale_factor=4), dict(rdn_config="B", scale=4)),
+    ("RDN", dict(rdn_config="A", scale_factor=2), dict(rdn_config="A", scale=2)),
+    ("SRCNN", dict(scale_factor=2), dict(scale=2)),
+])
+def test_state_shapes_match_the_plugin_modules(cls, kw, okw):
+    """oracle.sr_oracle.state_shapes (what bench.py's reference arm builds its weights from, without touching this repo's
+    models) lists the same keys, in the same order, with the same shapes as the drop-in modules — which
+    tests/test_boundary.py in turn pins to the live reference classes."""
+    import models
+    from oracle import sr_oracle
+    m = getattr(models, cls)(**kw)
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == list(sr_oracle.state_shapes(cls, **okw).items())
+    sd = sr_oracle.init_state(cls, seed=0, **okw)
+    m.load_state_dict(sd)       # loads: same dtypes / shapes, frozen MeanShift entries included
