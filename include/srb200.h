@@ -171,8 +171,10 @@ int  srb_wgrad_plan(int num_sms, int n, const int* ntiles, const int* k1, int* t
  * counters: n_ops * 2 * N int32, zero on entry. */
 enum { SRB_CHAIN_CONV = 0, SRB_CHAIN_CA_BWD = 1 };
 enum { SRB_CHAIN_CA = 32,              /* extra flag bits for SRB_CHAIN_CONV ops */
-       SRB_CHAIN_CA_BWD_FUSED = 64 };  /* after y is stored, run CA_BWD on it: g = y, t = tile e2, dt -> y2,
+       SRB_CHAIN_CA_BWD_FUSED = 64,    /* after y is stored, run CA_BWD on it: g = y, t = tile e2, dt -> y2,
                                           column sums of dt -> colsum2 (saves a whole dependent op per RCAB) */
+       SRB_CHAIN_Y_SCRATCH = 128 };    /* hint: nothing outside this chain reads slot y; a kernel that hands y to its
+                                          consumers on chip (conv_cluster.cu: TMEM-parked residual) may skip the store */
 #define SRB_CHAIN_NONE 0xFFFFu
 #define SRB_CHAIN_MAX_OPS 64
 

@@ -178,6 +178,67 @@ def stage_ca(shape):
     return ok
 
 
+def stage_rcab(shape, blocks=2):
+    """conv1+ReLU -> conv2+CALayer+skip, `blocks` times, then a plain conv: the CALayer gate is evaluated by the op BEFORE
+    the CALayer op (pool of a conv from its input's column sums) — against the per-layer kernels."""
+    n, h, w = shape
+    cr = 4
+    x = rnd((n, h, w, 64), seed=6).to(bf)
+    ws = [rnd((64, 64, 3, 3), 0.05, seed=50 + i).contiguous() for i in range(2 * blocks + 1)]
+    bs = [rnd((64,), 0.1, seed=70 + i) for i in range(2 * blocks + 1)]
+    cas = [(rnd((cr, 64), 0.2, seed=90 + 4 * i), rnd((cr,), 0.1, seed=91 + 4 * i), rnd((64, cr), 0.2, seed=92 + 4 * i),
+            rnd((64,), 0.1, seed=93 + 4 * i)) for i in range(blocks)]
+    packs = [ops.PackedWeights() for _ in ws]
+    cur = x
+    want = []
+    for b in range(blocks):
+        r = torch.empty_like(x)
+        ops.conv(cur, 0, 64, packs[2 * b], ws[2 * b], bs[2 * b], r, 0, 64, 3, relu=True)
+        t = torch.empty_like(x)
+        pool = torch.zeros(n, 64, device=DEV)
+        ops.conv(r, 0, 64, packs[2 * b + 1], ws[2 * b + 1], bs[2 * b + 1], t, 0, 64, 3, colsum=pool, colsum_groups=n)
+        out = torch.empty_like(x)
+        s = torch.empty(n, 64, device=DEV)
+        yg = torch.empty(n, 64, device=DEV)
+        ops.ca_fwd(t, cur, pool, False, *cas[b], out, s, yg)
+        want.append((r, t, out, pool, s, yg))
+        cur = out
+    last = torch.empty_like(x)
+    ops.conv(cur, 0, 64, packs[-1], ws[-1], bs[-1], last, 0, 64, 3, relu=True)
+    bank = ops.FilterBank().get(list(zip(ws, packs)), L.PACK_FWD)
+    A = torch.zeros((3 * blocks + 1, n, h, w, 64), dtype=bf, device=DEV)
+    pools = torch.zeros(blocks, n, 64, device=DEV)
+    ss = torch.empty(blocks, n, 64, device=DEV)
+    ys = torch.empty(blocks, n, 64, device=DEV)
+    ch = ops.Chain(n, h, w, x.device)
+    ch.space(0, A)
+    ch.space(1, x.view(1, n, h, w, 64))
+    ref = ops.Chain.ref
+    c = ref(1, 0)
+    for b in range(blocks):
+        ch.conv(c, ref(0, 3 * b), 2 * b, bs[2 * b], relu=True)
+        ch.conv_ca(ref(0, 3 * b), ref(0, 3 * b + 1), ref(0, 3 * b + 2), c, 2 * b + 1, bs[2 * b + 1], pools[b], *cas[b], ss[b], ys[b])
+        c = ref(0, 3 * b + 2)
+    ch.conv(c, ref(0, 3 * blocks), 2 * blocks, bs[-1], relu=True)
+    ch.run(bank)
+    torch.cuda.synchronize()
+    print(f"RCAB forward {shape} x{blocks}: cluster={ch.used_cluster}")
+    ok = True
+    for b in range(blocks):
+        r, t, out, pool, s, yg = want[b]
+        if b == 0:
+            ok &= where_bad(A[0], r, "block 0 relu conv")
+            ok &= where_bad(A[1], t, "block 0 t = conv2 + bias")
+        e = dict(r=rel(A[3 * b], r), t=rel(A[3 * b + 1], t), out=rel(A[3 * b + 2], out), pool=rel(pools[b], pool), s=rel(ss[b], s),
+                 gate=rel(ys[b], yg))
+        print(f"  block {b}: " + "  ".join(f"{k} rel {v:.2e}" for k, v in e.items()))
+        # the pool comes from the fp32 accumulators' linear form, the per-layer path pools the bf16-rounded t
+        ok &= e["pool"] < 5e-3 and e["s"] < 5e-3 and e["gate"] < 1e-3 and e["out"] < 4e-3 and e["t"] < 4e-3
+    e_last = rel(A[3 * blocks], last)
+    print(f"  last conv rel {e_last:.2e}")
+    return ok and e_last < 6e-3
+
+
 def stage_cabwd(shape):
     n, h, w = shape
     cr = 4
@@ -279,6 +340,9 @@ STAGES = {
     "ca6": lambda: stage_ca((16, 48, 48)),
     "cab1": lambda: stage_cabwd((2, 16, 24)),
     "cab6": lambda: stage_cabwd((16, 48, 48)),
+    "rcab1": lambda: stage_rcab((2, 16, 24)),
+    "rcab2": lambda: stage_rcab((2, 32, 48)),
+    "rcab6": lambda: stage_rcab((16, 48, 48), 3),
     "rcan": lambda: stage_model("rcan"),
     "edsr": lambda: stage_model("edsr"),
 }

@@ -50,6 +50,17 @@ def report(tr, n_ops, ctas, label, kinds=None):
     w = t[:, mid, 16:24] - t[:, mid, 9:10]
     print("  q1: acc1 -> tile-barrier arrive per epilogue warp (ns): " + " ".join(f"{x:.0f}" for x in w.mean(axis=(0, 1))))
     print(f"  q1: last warp arrive -> publisher released {(t[:, mid, 24] - t[:, mid, 16:24].max(axis=2)).mean():.0f} ns;  released -> arrives issued (lane 0) {(t[:, mid, 10] - t[:, mid, 24]).mean():.0f} ns, (lane 1) {(t[:, mid, 25] - t[:, mid, 24]).mean():.0f} ns")
+    if kinds is not None:      # timeline of every kind of op relative to its own mma:rdy0 (means over CTAs and middle ops)
+        names = {3: "issAll", 4: "acc0", 8: "pub0", 9: "acc1", 10: "pub1", 11: "acc2", 12: "pub2", 26: "ctaSums", 27: "vecReady",
+                 28: "matvec", 14: "gathered", 29: "sideDone", 13: "end"}
+        for k in sorted(set(kinds[:-1])):
+            sel = [i for i in range(n_ops // 4, 3 * n_ops // 4) if kinds[i] == k]
+            items = []
+            for e, nm in names.items():
+                v = t[:, sel, e]
+                if (v > 0).all():
+                    items.append((float((v - t[:, sel, 0]).mean()), nm))
+            print(f"  timeline {k}: " + "  ".join(f"{nm}={x:.0f}" for x, nm in sorted(items)))
     c = ctas // 2
     for op in range(n_ops // 2, n_ops // 2 + 2):
         base = t[c, op, 0]

@@ -300,14 +300,15 @@ class RCANGroupFn(Function):
                         db1=dcb1, dw2=dcw2.view(64, cr), db2=dcb2, scratch=scratch[b], colsum_dt=db2)
 
         # group tail conv: out = conv(last) + x; its input gradient is dL/dout of the last RCAB
-        ch.conv(ref(2, 0), ref(0, 3 * nb), 2 * nb, ca_bwd=ca_args(nb - 1))
+        # slots 3b+2 (b > 0) and 3nb hold dL/dout of an RCAB: read only as the residual two ops later, never by the host
+        ch.conv(ref(2, 0), ref(0, 3 * nb), 2 * nb, ca_bwd=ca_args(nb - 1), y_scratch=True)
         wq.append((A[3 * nb - 1], g, len(params) - 2, len(params) - 1))
         gref = ref(0, 3 * nb)
         for b in range(nb - 1, -1, -1):
             b1 = params[8 * b + 1]
             db1, grads[8 * b + 1] = _zeroed_grad_target(b1)
             ch.conv(ref(0, 3 * b), ref(0, 3 * b + 1), 2 * b + 1, mask=ref(1, 3 * b), colsum=db1, colsum_groups=1)
-            ch.conv(ref(0, 3 * b + 1), ref(0, 3 * b + 2), 2 * b, res=gref, ca_bwd=ca_args(b - 1) if b > 0 else None)
+            ch.conv(ref(0, 3 * b + 1), ref(0, 3 * b + 2), 2 * b, res=gref, ca_bwd=ca_args(b - 1) if b > 0 else None, y_scratch=b > 0)
             wq.append((A[3 * b], B[3 * b], 8 * b + 2, None))
             wq.append((A[3 * b - 1] if b > 0 else x, B[3 * b + 1], 8 * b, None))
             gref = ref(0, 3 * b + 2)

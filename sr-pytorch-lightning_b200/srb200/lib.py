@@ -41,6 +41,7 @@ class PackItem(C.Structure):
 CHAIN_CONV, CHAIN_CA_BWD = 0, 1
 CHAIN_CA = 32
 CHAIN_CA_BWD_FUSED = 64
+CHAIN_Y_SCRATCH = 128
 CHAIN_NONE = 0xFFFF
 CHAIN_MAX_OPS = 64
 

@@ -530,7 +530,7 @@ class Chain:
         return t.data_ptr()
 
     def conv(self, x, y, w_layer, bias=None, *, relu=False, scale=1.0, res=None, mask=None, colsum=None, colsum_groups=1,
-             colsum_scale=1.0, ca_bwd=None):
+             colsum_scale=1.0, ca_bwd=None, y_scratch=False):
         """ca_bwd: dict(t=ref, dt=ref, w1, b1, w2, b2, s, y, dw1, db1, dw2, db2, scratch, colsum_dt) — fuse the
         CALayer backward of the block whose dL/dout this conv produces (SRB_CHAIN_CA_BWD_FUSED)."""
         o = self._op(L.CHAIN_CONV, x, y)
@@ -545,6 +545,8 @@ class Chain:
             o.e = mask
         if ca_bwd is not None:
             o.flags |= L.CHAIN_CA_BWD_FUSED
+        if y_scratch:      # nothing outside the chain reads slot y (SRB_CHAIN_Y_SCRATCH)
+            o.flags |= L.CHAIN_Y_SCRATCH
         o.bias = self._ptr(bias)
         o.colsum = self._ptr(colsum)
         o.colsum_groups = colsum_groups
