@@ -136,6 +136,11 @@ typedef struct srb_wgrad_item {
   float* dbias;             /* may be NULL */
 } srb_wgrad_item;
 int  srb_conv_wgrad_batched(srb_ctx*, const srb_wgrad_item* items, int n, void* stream);
+/* max_ctas > 0: the batched weight-gradient launches of later srb_conv_wgrad_batched calls use at most that many CTAs
+ * (one per SM), so that they fit beside a kernel that leaves SMs free — the per-sample cluster chain (96 of 148 SMs for
+ * 16 x 48x48) on another stream; 0 restores "all SMs".  Replaces nothing in the reference: torch runs the weight
+ * gradients of a layer right behind its input gradient on the same stream (autograd engine). */
+int  srb_set_wgrad_sm_budget(srb_ctx*, int max_ctas);
 /* which kernel family (and hence which weight packing) backend AUTO resolves to */
 int  srb_conv_uses_umma(const srb_conv_desc*);
 int  srb_wgrad_uses_umma(const srb_wgrad_desc*);
@@ -210,6 +215,8 @@ typedef struct srb_chain_desc {
   int32_t* tile_flags;                /* NULL: layers are ordered by the per-sample counters; else n_ops * N * tiles int32, zero on
                                          entry (tiles = ceil(H/16) * ceil(W/8)): a tile waits only for the 3x3 neighbourhood of
                                          tiles of the previous op */
+  int32_t kernel_hint;                /* 0: the cluster kernel where it is eligible (see srb_conv_chain_uses_cluster); 1: always the
+                                         L2-flag kernel (all SMs, faster for forward chains that run alone); 2 = 0 */
 } srb_chain_desc;
 int  srb_conv_chain(srb_ctx*, const srb_chain_desc*, void* stream);
 /* 1 if srb_conv_chain runs this chain with the per-sample thread-block-cluster kernel (conv_cluster.cu: H % 16 == 0,

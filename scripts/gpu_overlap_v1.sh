@@ -1,0 +1,16 @@
+mkdir -p gpurun_out
+( timeout 900 python -m pytest tests/test_cluster_chain_gpu.py tests/test_trainer_gpu.py tests/test_runner_gpu.py tests/test_models_gpu.py -x -q 2>&1 | tail -5 ) | tee gpurun_out/overlap_tests.log
+summ='import json,sys
+for l in sys.stdin:
+    if l.startswith("{"):
+        d=json.loads(l); r=d["roofline"]; print(sys.argv[1], round(d["value"],1), round(d["ms_per_step"],3), "e2e", round(d["e2e"]["value"],1), "fwd", round(r["us_forward_launch"],1), "bwd", round(r["us_backward_launch"],1), "loss", d["config"]["loss_last"])'
+run() { name=$1; shift; env "$@" timeout 300 python bench.py --workload train --steps 20 --warmup 5 --no-cpu-baseline --no-extras --sustain-seconds 0.5 2>/dev/null | python -c "$summ" "$name" | tee -a gpurun_out/overlap_bench.log; }
+rm -f gpurun_out/overlap_bench.log
+run default A=1
+run no_overlap SRB200_WGRAD_OVERLAP=0
+run fwd_cluster SRB200_CHAIN_FWD=cluster
+run sms44_g8 SRB200_WGRAD_OVERLAP_SMS=44
+run sms52_g10 SRB200_WGRAD_OVERLAP_GROUPS=10
+run sms52_g6 SRB200_WGRAD_OVERLAP_GROUPS=6
+run sms36_g8 SRB200_WGRAD_OVERLAP_SMS=36
+run all_flags SRB200_CHAIN_CLUSTER=0

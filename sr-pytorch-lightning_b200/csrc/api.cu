@@ -35,6 +35,7 @@ extern "C" int srb_create(int device, srb_ctx** out) {
   srb_ctx* c = new srb_ctx();
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
+  c->wgrad_sm_budget = 0;
   c->smem_optin = (int)prop.sharedMemPerBlockOptin;
   c->encode_tiled = nullptr;
   c->weights_dirty = 1;
@@ -59,6 +60,11 @@ extern "C" int srb_destroy(srb_ctx* ctx) {
 }
 
 extern "C" int srb_num_sms(const srb_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
+extern "C" int srb_set_wgrad_sm_budget(srb_ctx* ctx, int max_ctas) {
+  if (!ctx || max_ctas < 0) return 1;
+  ctx->wgrad_sm_budget = max_ctas;
+  return 0;
+}
 
 /* diagnostics: conv_c64 writes 16 int64 per CTA (event clocks relative to CTA start, see conv_c64.cu)
  * into `buf` (device memory, >= 16 * num_sms int64) on every launch while it is set; NULL turns it off */

@@ -13,6 +13,7 @@ struct srb_ctx {
   int num_sms;
   int smem_optin;
   void* encode_tiled;  // PFN_cuTensorMapEncodeTiled, resolved at srb_create
+  int wgrad_sm_budget; // > 0: batched weight-gradient launches use at most this many CTAs (srb_set_wgrad_sm_budget)
   int weights_dirty;   // a pack kernel was launched since the last fully serialised conv launch (conv_c64.cu)
   long long* trace;    // diagnostics: device buffer for per-CTA event clocks of conv_c64 (NULL = off)
   int no_pdl;          // SRB200_NO_PDL=1: never use programmatic dependent launch (A/B measurements)

@@ -50,8 +50,6 @@ constexpr int kMaxCr = 16;
 constexpr int kMaxCluster = 8;
 constexpr uint32_t kScaled = 1u << 16;    // epilogue specialisation keys: scale != 1 / no specialisation
 constexpr uint32_t kGeneric = 1u << 17;
-constexpr uint32_t kPool = 1u << 18;      // accumulate the column sums of the stored values for the next op's CALayer gate
-constexpr uint32_t kField = 1u << 19;     // add the position-class bias (conv of a constant field)
 
 enum { RES_NONE = 0, RES_INPLACE = 1, RES_TMEM = 2, RES_GLOBAL = 3 };
 
@@ -72,13 +70,6 @@ struct COp {
   uint8_t res_mode;      // RES_*
   uint8_t park;          // keep the packed result y in TMEM for the op after next (its residual)
   uint16_t y_ref, y2_ref;   // (space << 14) | slot of y / y2 for the TMA row stores
-  uint8_t pre_pool;      // plain conv whose consumer is a CALayer op: after its tiles, evaluate that op's gate from the column
-                         // sums of this op's output (the pool of a conv is linear in its input, see the kernel)
-  uint8_t pooled;        // CALayer op whose gate the previous op has already evaluated: single-pass epilogue
-  uint8_t defer;         // CA_BWD_FUSED op followed by a plain conv: publish g*gate at once, fold ds/HW into the consumer
-  uint8_t field;         // plain conv whose input misses a per-channel constant (ds/HW): add its conv as a position-class bias
-  uint8_t skip_y;        // y is consumed on chip only (TMEM-parked residual): no global store
-  uint8_t pad[3];
 };
 
 struct CParams {
@@ -109,14 +100,10 @@ struct Small {
   uint64_t ready[2][2];          // [buffer][A / B]
   uint64_t pool_full[2];
   uint32_t tmem_slot, pad;
-  alignas(16) float bias[2][64];
+  float bias[2][64];
   float wsum[8][32];
   float pool[2][kMaxCluster][64];
-  alignas(16) float ca_s[64], ca_y[64], ca_du[64], ca_ds[64], ca_tot[64], ca_z[kMaxCr], ca_dv[kMaxCr];
-  alignas(16) float bsum[4][64]; // column sums over the image-border pixels of this CTA: top row, bottom row, left, right column
-  float sv[9][64];               // forward: per-tap input sums S_tap[cin]; backward: V_tap[cout] = W_tap . ds/HW  (tap = kw*3 + kh)
-  float bc[9][64];               // backward: conv of the constant field ds/HW per position class (row class * 3 + column class)
-  float pm[4][64];               // partial dot products of the pool mat-vec
+  float ca_s[64], ca_y[64], ca_du[64], ca_ds[64], ca_tot[64], ca_z[kMaxCr], ca_dv[kMaxCr];
 };
 
 constexpr uint32_t kSmemBytes = kWBytes + 2u * kXStride + kEBytes + (uint32_t)sizeof(Small) + 1024u;
@@ -283,13 +270,6 @@ __device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lan
   return v[0];
 }
 
-// eight consecutive per-channel constants from shared memory with two 16-byte loads (every shared-memory instruction of
-// the epilogue competes with the MMAs' operand fetch for the same port: 32 scalar loads per tile were 0.6 us)
-__device__ __forceinline__ void load8(const float* p, float (&o)[8]) {
-  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
-}
-
 __device__ __forceinline__ void unpack4(const uint4 (&ev)[4], float (&f)[32]) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -327,7 +307,7 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
   if (threadIdx.x == 0) {
     for (int i = 0; i < 3; ++i) {
       ptx::mbar_init(&S.w_full[i], 1);
-      ptx::mbar_init(&S.w_empty[i], 2);       // the MMA commit + the epilogue (it may read the filters too, see pre_pool / defer)
+      ptx::mbar_init(&S.w_empty[i], 1);
     }
     for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(&S.acc_full[i], 1);
@@ -595,17 +575,12 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
       return (S.wsum[hh * 4][ch] + S.wsum[hh * 4 + 1][ch]) + (S.wsum[hh * 4 + 2][ch] + S.wsum[hh * 4 + 3][ch]);
     };
     // 64 per-CTA sums -> every CTA of the cluster gets all of them; the sample total lands in S.ca_tot
-    auto all_gather = [&](const float part) {      // part: this CTA's value of channel et (threads et < 64)
+    auto all_gather = [&]() {
       const uint32_t par = ca_count & 1u, ph = (ca_count >> 1) & 1u;
       if (et < 64) {
-        // four channels per remote store: 16 lanes x csize 16-byte st.async instead of 64 x csize 4-byte ones
-        const float p1 = __shfl_down_sync(0xffffffffu, part, 1), p2 = __shfl_down_sync(0xffffffffu, part, 2),
-                    p3 = __shfl_down_sync(0xffffffffu, part, 3);
-        if ((lane & 3) == 0) {
-          const uint4 v = make_uint4(__float_as_uint(part), __float_as_uint(p1), __float_as_uint(p2), __float_as_uint(p3));
-          const uint32_t slot = ptx::smem_u32(&S.pool[par][rank][et]);
-          for (int r = 0; r < csize; ++r) st_async_v4(mapa(slot, (uint32_t)r), v, mapa(pool_bar0 + par * 8u, (uint32_t)r));
-        }
+        const float part = cta_total(et);
+        const uint32_t slot = ptx::smem_u32(&S.pool[par][rank][et]);
+        for (int r = 0; r < csize; ++r) st_async_b32(mapa(slot, (uint32_t)r), __float_as_uint(part), mapa(pool_bar0 + par * 8u, (uint32_t)r));
       }
       if (et == 64) ptx::mbar_arrive_expect_tx(&S.pool_full[par], (uint32_t)csize * 256u);     // 64 floats from every CTA of the cluster
       mbar_wait_cluster(&S.pool_full[par], ph);
@@ -618,39 +593,6 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
       ptx::named_bar_sync(1, kEpi);
     };
 
-    // one bf16 channel of pixel idx (= row * kXW + column) of an activation buffer
-    auto x_value = [&](const uint32_t xb, const uint32_t idx, const int ch) {
-      const uint32_t a = xb + idx * 128u + ((((uint32_t)ch >> 3) ^ (idx & 7u)) << 4) + ((uint32_t)ch & 7u) * 2u;
-      uint16_t r;
-      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(a) : "memory");
-      return __uint_as_float((uint32_t)r << 16);
-    };
-    // the filters of the NEXT op (already requested by the filter producer) as seen by generic loads
-    auto wait_next_filters = [&](const int op_next) {
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) ptx::mbar_wait(&S.w_full[kw], (uint32_t)op_next & 1u);
-    };
-    auto release_next_filters = [&]() {      // after a barrier that follows the reads
-      if (et == 64) {
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) ptx::mbar_arrive(&S.w_empty[kw]);
-      }
-    };
-    // 16-byte piece `chunk` (8 input channels) of filter row (tap = kw*3 + kh, cout) in the swizzled slab layout
-    auto filter_chunk = [&](const int tap, const int cout, const int chunk) {
-      const int kw = tap / 3, kh = tap - 3 * kw;
-      return ptx::lds128(wbase + (uint32_t)kw * kSlabBytes + (uint32_t)kh * 8192u + (uint32_t)cout * 128u +
-                         ((uint32_t)(chunk ^ (cout & 7)) << 4));
-    };
-    auto dot8 = [&](const uint4 wv, const float* x8, float a) {
-      const float4 x0 = *reinterpret_cast<const float4*>(x8), x1 = *reinterpret_cast<const float4*>(x8 + 4);
-      const float2 w0 = unpack_bf16x2(wv.x), w1 = unpack_bf16x2(wv.y), w2 = unpack_bf16x2(wv.z), w3 = unpack_bf16x2(wv.w);
-      float b = w2.x * x1.x;
-      a = fmaf(w0.x, x0.x, a); b = fmaf(w2.y, x1.y, b); a = fmaf(w0.y, x0.y, a); b = fmaf(w3.x, x1.z, b);
-      a = fmaf(w1.x, x0.z, a); b = fmaf(w3.y, x1.w, b); a = fmaf(w1.y, x0.w, a);
-      return a + b;
-    };
-
     for (int op = 0; op < p.n_ops; ++op) {
       const COp& o = p.ops[op];
       const uint32_t flags = o.flags;
@@ -658,20 +600,6 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
       const int bsel = op & 1;
       const int res_mode = o.res_mode;
       if (et < 64) S.bias[bsel][et] = o.bias ? __ldg(o.bias + et) : 0.f;
-      // filter slabs are released by the MMA commit AND by the epilogue: ops whose filters the epilogue reads itself (the pool /
-      // constant-field mat-vecs of pooled / field ops) were released by the previous op's epilogue after those reads
-      if (et == 64 && !(o.pooled | o.field)) {
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) ptx::mbar_arrive(&S.w_empty[kw]);
-      }
-      if (o.defer) {
-        if (et < 64) {
-          S.ca_s[et] = o.ca_s[(size_t)n * 64 + et];      // written by the forward launch
-          S.ca_y[et] = o.ca_y[(size_t)n * 64 + et];
-        }
-        // no TMA row store is in flight while this op runs (it issues none itself): X[ob] may be rewritten freely
-        if (h == 0 && lane < 4) ptx::bulk_wait_group_read<0>();
-      }
       ptx::named_bar_sync(1, kEpi);
       const float* bias_h = &S.bias[bsel][h * 32];
       const float scale = o.scale;
@@ -730,8 +658,7 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
         // ---------------- plain conv: bias, ReLU, scale, mask or residual (arithmetic = conv_chain.cu) ----------------
         auto tile = [&](auto FC, const int q) {
           constexpr uint32_t FK = decltype(FC)::value;
-          const uint32_t F = (FK == kGeneric) ? ((flags & 15u) | kScaled | (o.pre_pool ? kPool : 0u) | (o.field ? kField : 0u))
-                                              : FK;     // compile-time constant unless generic
+          const uint32_t F = (FK == kGeneric) ? ((flags & 15u) | kScaled) : FK;     // compile-time constant unless generic
           const int j = mirror ? 2 - q : q;
           uint4 ev[4];
           if (F & SRB_MASK) take_operand(ev);
@@ -742,16 +669,6 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
           load_acc(q, v, true);
           if (et == 0 && q == 0) CL_TRACE(op, 5);
           add_bias(v);
-          if (F & kField) {              // + conv(constant field ds/HW) at this pixel's position class
-            const int gy = band * 16 + ty, gx = f * 24 + 8 * j + tx;
-            const int cls = (gy == 0 ? 0 : (gy == p.H - 1 ? 2 : 1)) * 3 + (gx == 0 ? 0 : (gx == p.W - 1 ? 2 : 1));
-            const float* bch = &S.bc[cls][h * 32];
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 bq = *reinterpret_cast<const float4*>(bch + i);
-              v[i] += bq.x; v[i + 1] += bq.y; v[i + 2] += bq.z; v[i + 3] += bq.w;
-            }
-          }
           if (F & SRB_RELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -778,7 +695,7 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
           for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
           if (o.park) park(pk, q);
           store_x(pk, j, q, ob);
-          if (F & (SRB_COLSUM | kPool)) {          // sums of the STORED (bf16-rounded) values, as the other conv kernels
+          if (F & SRB_COLSUM) {          // sums of the STORED (bf16-rounded) values, as the other conv kernels
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float2 fr = unpack_bf16x2(pk[i]);
@@ -794,10 +711,8 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
 #pragma unroll 1
           for (int q = 0; q < 3; ++q) tile(FC, q);
         };
-        switch ((flags & 15u) | (scale != 1.f ? kScaled : 0u) | (o.pre_pool ? kPool : 0u) | (o.field ? kField : 0u)) {
+        switch ((flags & 15u) | (scale != 1.f ? kScaled : 0u)) {
           case SRB_RELU: run(std::integral_constant<uint32_t, SRB_RELU>{}); break;
-          case SRB_RELU | kPool: run(std::integral_constant<uint32_t, SRB_RELU | kPool>{}); break;
-          case SRB_MASK | SRB_COLSUM | kField: run(std::integral_constant<uint32_t, SRB_MASK | SRB_COLSUM | kField>{}); break;
           case SRB_RESIDUAL: run(std::integral_constant<uint32_t, SRB_RESIDUAL>{}); break;
           case SRB_RESIDUAL | kScaled: run(std::integral_constant<uint32_t, SRB_RESIDUAL | kScaled>{}); break;
           case SRB_RESIDUAL | SRB_COLSUM: run(std::integral_constant<uint32_t, SRB_RESIDUAL | SRB_COLSUM>{}); break;
@@ -812,169 +727,6 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
           if (et < 64) {
             const float tot = cta_total(et);
             atomicAdd(o.colsum + (size_t)(o.colsum_groups > 1 ? n : 0) * 64 + et, o.colsum_scale != 0.f ? tot * o.colsum_scale : tot);
-          }
-        }
-        if (o.pre_pool) {
-          // ---- gate of the NEXT op (RCAB conv2 + CALayer) from THIS op's output r, while that op's MMAs run ----
-          // mean_p(conv2(r) + b)[c] = b[c] + 1/HW sum_{tap,ci} W2[tap][c][ci] * S_tap[ci], where S_tap[ci] sums r[., ci] over the
-          // pixels tap reads for SOME output pixel: all of the image minus the row / column that zero padding replaces
-          // (kh = 2 never reads the top row, kh = 0 never the bottom row, kw = 2 / 0 the left / right column).  Every CTA
-          // applies the mat-vec to the sums over its own pixels; the 64 partial pools are then all-gathered as before.
-          const COp& o2 = p.ops[op + 1];
-          const int Cr = o2.ca_cr;
-          const bool fast = Cr <= 4;
-          if (!(flags & SRB_COLSUM)) reduce_cta(rs);          // S.wsum: totals over this CTA's 16 x 24 pixels (barrier inside)
-          if (et == 0) CL_TRACE(op, 26);
-          const uint32_t xo = xbase + (uint32_t)ob * kXStride;
-          {
-            const int vec = et >> 6, ch = et & 63;
-            const bool have = vec == 0 ? band == 0 : (vec == 1 ? band == bands - 1 : (vec == 2 ? f == 0 : f == halves - 1));
-            float a = 0.f;
-            if (have) {
-              float a1 = 0.f, a2 = 0.f, a3 = 0.f;
-              if (vec < 2) {
-                const uint32_t r0 = (uint32_t)((vec == 0 ? 1 : 16) * kXW + 1);
-#pragma unroll
-                for (uint32_t c = 0; c < 24u; c += 4) {
-                  a += x_value(xo, r0 + c, ch); a1 += x_value(xo, r0 + c + 1, ch);
-                  a2 += x_value(xo, r0 + c + 2, ch); a3 += x_value(xo, r0 + c + 3, ch);
-                }
-              } else {
-                const uint32_t c0 = (uint32_t)(kXW + (vec == 2 ? 1 : 24));
-#pragma unroll
-                for (uint32_t r = 0; r < 16u; r += 4) {
-                  a += x_value(xo, c0 + r * (uint32_t)kXW, ch); a1 += x_value(xo, c0 + (r + 1) * (uint32_t)kXW, ch);
-                  a2 += x_value(xo, c0 + (r + 2) * (uint32_t)kXW, ch); a3 += x_value(xo, c0 + (r + 3) * (uint32_t)kXW, ch);
-                }
-              }
-              a = (a + a1) + (a2 + a3);
-            }
-            S.bsum[vec][ch] = a;
-          }
-          // gate operands do not depend on the sums: fetch them now
-          float w1a = 0.f, w1b = 0.f, b1v = 0.f;
-          if (fast && w8 < Cr) {
-            w1a = __ldg(o2.ca_w1 + w8 * 64 + lane);
-            w1b = __ldg(o2.ca_w1 + w8 * 64 + lane + 32);
-            b1v = __ldg(o2.ca_b1 + w8);
-          }
-          float w2r[4] = {0.f, 0.f, 0.f, 0.f}, b2v = 0.f, cbias = 0.f;
-          if (et < 64) {
-            b2v = __ldg(o2.ca_b2 + et);
-            cbias = o2.bias ? __ldg(o2.bias + et) : 0.f;
-            if (fast)
-              for (int jj = 0; jj < Cr; ++jj) w2r[jj] = __ldg(o2.ca_w2 + et * Cr + jj);
-          }
-          ptx::named_bar_sync(1, kEpi);
-          for (int i = et; i < 9 * 64; i += kEpi) {
-            const int tap = i >> 6, ci = i & 63, kw = tap / 3, kh = tap - 3 * kw;
-            float sacc = cta_total(ci);
-            if (kh == 2) sacc -= S.bsum[0][ci];
-            if (kh == 0) sacc -= S.bsum[1][ci];
-            if (kw == 2) sacc -= S.bsum[2][ci];
-            if (kw == 0) sacc -= S.bsum[3][ci];
-            if (kh == 2 && kw == 2 && band == 0 && f == 0) sacc += x_value(xo, (uint32_t)(kXW + 1), ci);
-            if (kh == 2 && kw == 0 && band == 0 && f == halves - 1) sacc += x_value(xo, (uint32_t)(kXW + 24), ci);
-            if (kh == 0 && kw == 2 && band == bands - 1 && f == 0) sacc += x_value(xo, (uint32_t)(16 * kXW + 1), ci);
-            if (kh == 0 && kw == 0 && band == bands - 1 && f == halves - 1) sacc += x_value(xo, (uint32_t)(16 * kXW + 24), ci);
-            S.sv[tap][ci] = sacc;
-          }
-          wait_next_filters(op + 1);
-          ptx::named_bar_sync(1, kEpi);
-          if (et == 0) CL_TRACE(op, 27);
-          {
-            const int c = et & 63, part = et >> 6;          // output channel, quarter of the input channels
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-#pragma unroll
-            for (int tap = 0; tap < 9; tap += 3) {
-#pragma unroll
-              for (int k2 = 0; k2 < 2; ++k2) {
-                a0 = dot8(filter_chunk(tap, c, part * 2 + k2), &S.sv[tap][(part * 2 + k2) * 8], a0);
-                a1 = dot8(filter_chunk(tap + 1, c, part * 2 + k2), &S.sv[tap + 1][(part * 2 + k2) * 8], a1);
-                a2 = dot8(filter_chunk(tap + 2, c, part * 2 + k2), &S.sv[tap + 2][(part * 2 + k2) * 8], a2);
-              }
-            }
-            S.pm[part][c] = (a0 + a1) + a2;
-          }
-          ptx::named_bar_sync(1, kEpi);
-          if (et == 0) CL_TRACE(op, 28);
-          release_next_filters();
-          all_gather(et < 64 ? (S.pm[0][et] + S.pm[1][et]) + (S.pm[2][et] + S.pm[3][et]) : 0.f);
-          if (et == 0) CL_TRACE(op, 14);
-          if (et < 64) {
-            const float tot = fmaf((float)(p.H * p.W), cbias, S.ca_tot[et]);      // sum over the sample of t = conv + bias
-            S.ca_s[et] = tot * inv_hw;
-            if (rank == 0) {
-              o2.colsum[(size_t)n * 64 + et] = tot;
-              o2.ca_s[(size_t)n * 64 + et] = tot * inv_hw;
-            }
-          }
-          ptx::named_bar_sync(1, kEpi);
-          if (fast) {
-            if (w8 < Cr) {
-              const float a = warp_sum(w1a * S.ca_s[lane] + w1b * S.ca_s[lane + 32]);
-              if (lane == 0) S.ca_z[w8] = fmaxf(a + b1v, 0.f);
-            }
-          } else {
-            for (int jj = w8; jj < Cr; jj += 8) {
-              const float a = warp_sum(__ldg(o2.ca_w1 + jj * 64 + lane) * S.ca_s[lane] + __ldg(o2.ca_w1 + jj * 64 + lane + 32) * S.ca_s[lane + 32]);
-              if (lane == 0) S.ca_z[jj] = fmaxf(a + __ldg(o2.ca_b1 + jj), 0.f);
-            }
-          }
-          ptx::named_bar_sync(1, kEpi);
-          if (et < 64) {
-            float u = b2v;
-            for (int jj = 0; jj < Cr; ++jj) u += (fast ? w2r[jj & 3] : __ldg(o2.ca_w2 + et * Cr + jj)) * S.ca_z[jj];
-            const float yv = 1.f / (1.f + expf(-u));
-            S.ca_y[et] = yv;
-            if (rank == 0) o2.ca_y[(size_t)n * 64 + et] = yv;
-          }
-          ptx::named_bar_sync(1, kEpi);
-          if (et == 0) CL_TRACE(op, 29);
-        }
-      } else if ((flags & SRB_CHAIN_CA) && o.pooled) {
-        // ---------------- RCAB conv2 + CALayer + skip, gate known (evaluated under this op's MMAs): one pass ----------------
-        const float* yh = &S.ca_y[h * 32];
-#pragma unroll 1
-        for (int q = 0; q < 3; ++q) {
-          const int j = mirror ? 2 - q : q;
-          // the staging tile's rows of the previous position have left (TMA row stores) before they are rewritten
-          if (h == 0 && lane < 4) ptx::bulk_wait_group_read<0>();
-          ptx::named_bar_sync(kBarPair + quarter, 64);
-          uint4 ev[4];
-          fetch_residual(ev, q, j);
-          wait_acc(q);
-          if (et == 0) CL_TRACE(op, q == 0 ? 4 : (q == 1 ? 9 : 11));
-          float v[32];
-          load_acc(q, v, true);
-          add_bias(v);
-          uint32_t pk[16];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint32_t xw[4] = {ev[g].x, ev[g].y, ev[g].z, ev[g].w};
-            uint32_t pt[4];
-            float y8[8];
-            load8(yh + g * 8, y8);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              pt[e] = pack_bf16x2(v[g * 8 + e * 2], v[g * 8 + e * 2 + 1]);      // t as stored
-              const float2 ft = unpack_bf16x2(pt[e]);
-              const float2 fx = unpack_bf16x2(xw[e]);
-              pk[g * 4 + e] = pack_bf16x2(fmaf(ft.x, y8[e * 2], fx.x), fmaf(ft.y, y8[e * 2 + 1], fx.y));
-            }
-            ptx::sts128(el + (((uint32_t)(h * 4 + g) ^ (uint32_t)tx) << 4), make_uint4(pt[0], pt[1], pt[2], pt[3]));
-          }
-          if (o.park) park(pk, q);
-          store_x(pk, j, q, ob);
-          publish(q, op);
-          // rows of X[ob] (out) and of the staging tile (t) -> global: the two warps of a lane quarter wrote the same four rows
-          ptx::named_bar_sync(kBarPair + quarter, 64);
-          if (h == 0 && lane < 4) {
-            const int trow = quarter * 4 + lane;
-            const uint32_t src = xbase + (uint32_t)ob * kXStride + (uint32_t)((trow + 1) * kXW + 1 + 8 * j) * 128u;
-            tma_store_5d(&maps.row[o.y2_ref >> 14], src, 0, f * 24 + 8 * j, band * 16 + trow, n, o.y2_ref & 0x3FFF);
-            tma_store_5d(&maps.row[o.y_ref >> 14], ebase + (uint32_t)trow * 1024u, 0, f * 24 + 8 * j, band * 16 + trow, n, o.y_ref & 0x3FFF);
-            ptx::bulk_commit_group();
           }
         }
       } else if (flags & SRB_CHAIN_CA) {
@@ -1020,7 +772,7 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
             for (int jj = 0; jj < Cr; ++jj) w2r[jj] = __ldg(o.ca_w2 + et * Cr + jj);
         }
         reduce_cta(rs);
-        all_gather(et < 64 ? cta_total(et) : 0.f);
+        all_gather();
         if (et == 0) CL_TRACE(op, 14);
         if (et < 64) {
           const float tot = S.ca_tot[et];
@@ -1066,13 +818,11 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
           for (int g = 0; g < 4; ++g) {
             const uint32_t xw[4] = {ev[g].x, ev[g].y, ev[g].z, ev[g].w};
 #pragma unroll
-            float y8[8];
-            load8(yh + g * 8, y8);
-#pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 ft = unpack_bf16x2(pack_bf16x2(v[g * 8 + e * 2], v[g * 8 + e * 2 + 1]));   // t as stored
               const float2 fx = unpack_bf16x2(xw[e]);
-              pk[g * 4 + e] = pack_bf16x2(fmaf(ft.x, y8[e * 2], fx.x), fmaf(ft.y, y8[e * 2 + 1], fx.y));
+              const int ch = g * 8 + e * 2;
+              pk[g * 4 + e] = pack_bf16x2(fmaf(ft.x, yh[ch], fx.x), fmaf(ft.y, yh[ch + 1], fx.y));
             }
           }
           if (o.park) park(pk, q);
@@ -1080,205 +830,6 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
           publish(q, op);
           store_rows(o.y2_ref, j, ob);
         }
-      } else if (o.defer) {
-        // ---------------- dgrad conv (+ residual) + CALayer backward, sample-wide reduction OFF the chain's critical path --------
-        // dt = g * gate + ds/HW, and ds needs sum_p g*t over the whole sample.  The consumer (a conv) is linear, so this op
-        // publishes g * gate at once and the consumer adds conv(constant field ds/HW) — a per-output-channel constant per
-        // position class (interior / edges / corners, because of the zero padding) — in its epilogue (COp::field).  The
-        // all-gather, the gate backward and that 64 x 576 mat-vec run here under the consumer's MMAs; the true dt goes to
-        // global memory (weight gradients, bias gradient) from a second sweep over X[ob].
-        const COp& o2 = p.ops[op + 1];
-        const int Cr = o.ca_cr;
-        const bool fast = Cr <= 4;
-        const bool has_res = (flags & SRB_RESIDUAL) != 0;
-        const float* yh = &S.ca_y[h * 32];
-#pragma unroll 1
-        for (int q = 0; q < 3; ++q) {
-          const int j = mirror ? 2 - q : q;
-          uint4 ev[4], tv[4];
-          take_operand(tv);
-          if (has_res) fetch_residual(ev, q, j);
-          wait_acc(q);
-          if (et == 0) CL_TRACE(op, q == 0 ? 4 : (q == 1 ? 9 : 11));
-          float v[32];
-          load_acc(q, v, true);
-          add_bias(v);
-          if (scale != 1.f) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= scale;
-          }
-          if (has_res) {
-            float fr[32];
-            unpack4(ev, fr);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += fr[i];
-          }
-          uint32_t pk[16], pg[16];
-          {
-            float ft[32];
-            unpack4(tv, ft);
-#pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
-              float y8[8];
-              load8(yh + g8 * 8, y8);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int i = g8 * 4 + e;
-                pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);              // g as stored
-                const float2 fg = unpack_bf16x2(pk[i]);
-                rs[2 * i] = fmaf(fg.x, ft[2 * i], rs[2 * i]);
-                rs[2 * i + 1] = fmaf(fg.y, ft[2 * i + 1], rs[2 * i + 1]);
-                pg[i] = pack_bf16x2(fg.x * y8[2 * e], fg.y * y8[2 * e + 1]);      // g * gate: what the consumer convolves
-              }
-            }
-          }
-          park(pk, q);                   // g stays on chip: the residual two ops later (if any) and the dt sweep below
-          store_x(pg, j, q, ob);
-          publish(q, op);
-          if (!o.skip_y) {
-            uint8_t* dst = o.y + goff0 + (size_t)j * 1024u;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) stg128(dst + g * 16, make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]));
-          }
-        }
-        // everything the gate backward needs that does not depend on the sample sums
-        float w1a = 0.f, w1b = 0.f, b1v = 0.f, w2a = 0.f, w2b = 0.f;
-        if (fast && w8 < Cr) {
-          w1a = __ldg(o.ca_w1 + w8 * 64 + lane);
-          w1b = __ldg(o.ca_w1 + w8 * 64 + lane + 32);
-          b1v = __ldg(o.ca_b1 + w8);
-          w2a = __ldg(o.ca_w2 + lane * Cr + w8);
-          w2b = __ldg(o.ca_w2 + (lane + 32) * Cr + w8);
-        }
-        float w2r[4] = {0.f, 0.f, 0.f, 0.f}, w1c[4] = {0.f, 0.f, 0.f, 0.f}, b2v = 0.f;
-        if (et < 64) {
-          b2v = __ldg(o.ca_b2 + et);
-          if (fast)
-            for (int jj = 0; jj < Cr; ++jj) {
-              w2r[jj] = __ldg(o.ca_w2 + et * Cr + jj);
-              w1c[jj] = __ldg(o.ca_w1 + jj * 64 + et);
-            }
-        }
-        reduce_cta(rs);
-        if (fast) {
-          if (w8 < Cr) {
-            float a = warp_sum(w1a * S.ca_s[lane] + w1b * S.ca_s[lane + 32]);
-            if (lane == 0) {
-              a += b1v;
-              S.ca_z[w8] = fmaxf(a, 0.f);
-              S.ca_dv[w8] = a > 0.f ? 1.f : 0.f;
-            }
-          }
-        } else {
-          for (int jj = w8; jj < Cr; jj += 8) {
-            float a = warp_sum(__ldg(o.ca_w1 + jj * 64 + lane) * S.ca_s[lane] + __ldg(o.ca_w1 + jj * 64 + lane + 32) * S.ca_s[lane + 32]);
-            if (lane == 0) {
-              a += __ldg(o.ca_b1 + jj);
-              S.ca_z[jj] = fmaxf(a, 0.f);
-              S.ca_dv[jj] = a > 0.f ? 1.f : 0.f;
-            }
-          }
-        }
-        all_gather(et < 64 ? cta_total(et) : 0.f);        // (barriers: ca_z / ca_dv visible, S.ca_tot = sum g*t over the sample)
-        if (et == 0) CL_TRACE(op, 14);
-        if (et < 64) {
-          float u = b2v;
-          for (int jj = 0; jj < Cr; ++jj) u += (fast ? w2r[jj & 3] : __ldg(o.ca_w2 + et * Cr + jj)) * S.ca_z[jj];
-          const float sp = 1.f / (1.f + expf(-u)), sn = 1.f / (1.f + expf(u));
-          S.ca_du[et] = S.ca_tot[et] * (sp * sn);         // sigmoid'(u) from u itself
-        }
-        ptx::named_bar_sync(1, kEpi);
-        if (fast) {
-          if (w8 < Cr) {
-            const float dz = warp_sum(w2a * S.ca_du[lane] + w2b * S.ca_du[lane + 32]);
-            if (lane == 0) S.ca_dv[w8] *= dz;
-          }
-        } else {
-          for (int jj = w8; jj < Cr; jj += 8) {
-            const float dz = warp_sum(__ldg(o.ca_w2 + lane * Cr + jj) * S.ca_du[lane] + __ldg(o.ca_w2 + (lane + 32) * Cr + jj) * S.ca_du[lane + 32]);
-            if (lane == 0) S.ca_dv[jj] *= dz;
-          }
-        }
-        ptx::named_bar_sync(1, kEpi);
-        if (et < 64) {
-          float d = 0.f;
-          for (int jj = 0; jj < Cr; ++jj) d += (fast ? w1c[jj & 3] : __ldg(o.ca_w1 + jj * 64 + et)) * S.ca_dv[jj];
-          S.ca_ds[et] = d * inv_hw;
-        }
-        if (rank == 0) {                                  // parameter gradients, once per sample
-          for (int i = et; i < 64 * Cr; i += kEpi) {
-            atomicAdd(o.ca_dw2 + i, S.ca_du[i / Cr] * S.ca_z[i % Cr]);     // w2 [64][Cr]
-            atomicAdd(o.ca_dw1 + i, S.ca_dv[i / 64] * S.ca_s[i % 64]);     // w1 [Cr][64]
-          }
-          if (et < 64) atomicAdd(o.ca_db2 + et, S.ca_du[et]);
-          if (et < Cr) atomicAdd(o.ca_db1 + et, S.ca_dv[et]);
-        }
-        wait_next_filters(op + 1);
-        ptx::named_bar_sync(1, kEpi);                     // S.ca_ds complete
-        if (et == 0) CL_TRACE(op, 27);
-        // V_tap[co] = sum_c W[tap][co][c] * ds[c]/HW with the consumer's filters
-        for (int i = et; i < 9 * 64; i += kEpi) {
-          const int tap = i >> 6, co = i & 63;
-          float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-          for (int k = 0; k < 8; k += 2) {
-            a0 = dot8(filter_chunk(tap, co, k), &S.ca_ds[k * 8], a0);
-            a1 = dot8(filter_chunk(tap, co, k + 1), &S.ca_ds[(k + 1) * 8], a1);
-          }
-          S.sv[tap][co] = a0 + a1;
-        }
-        ptx::named_bar_sync(1, kEpi);
-        if (et == 0) CL_TRACE(op, 28);
-        release_next_filters();
-        // position classes: a pixel in the top image row never sees kh = 0 (it would read row -1), the bottom row never kh = 2,
-        // the left / right column never kw = 0 / kw = 2
-        for (int i = et; i < 9 * 64; i += kEpi) {
-          const int cls = i >> 6, co = i & 63, rc = cls / 3, cc = cls - 3 * rc;
-          float a = 0.f;
-#pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            if ((cc == 0 && kw == 0) || (cc == 2 && kw == 2)) continue;
-#pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-              if ((rc == 0 && kh == 0) || (rc == 2 && kh == 2)) continue;
-              a += S.sv[kw * 3 + kh][co];
-            }
-          }
-          S.bc[cls][co] = a;
-        }
-        // the true dt = g*gate + ds/HW -> global (weight / bias gradients of the conv that produced t), column sums of dt
-        const float* dsh = &S.ca_ds[h * 32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) rs[i] = 0.f;
-        uint8_t* const dtg = o.y2 + goff0;
-#pragma unroll 1
-        for (int q = 0; q < 3; ++q) {
-          const int j = mirror ? 2 - q : q;
-          uint32_t g16[16];
-          tmem_ld_x16(park_addr(op & 1, q), g16);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint32_t pd[4];
-            float y8[8], d8[8];
-            load8(yh + g * 8, y8);
-            load8(dsh + g * 8, d8);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 fg = unpack_bf16x2(g16[g * 4 + e]);
-              const int ch = g * 8 + e * 2;
-              pd[e] = pack_bf16x2(fmaf(fg.x, y8[e * 2], d8[e * 2]), fmaf(fg.y, y8[e * 2 + 1], d8[e * 2 + 1]));      // as the two-pass form
-              const float2 fd = unpack_bf16x2(pd[e]);
-              rs[ch] += fd.x;
-              rs[ch + 1] += fd.y;
-            }
-            stg128(dtg + (size_t)j * 1024u + g * 16, make_uint4(pd[0], pd[1], pd[2], pd[3]));
-          }
-        }
-        if (et == 0) CL_TRACE(op, 29);
-        reduce_cta(rs);                                   // (barrier: S.bc complete before the consumer's epilogue reads it)
-        if (o.colsum2 && et < 64) atomicAdd(o.colsum2 + et, cta_total(et));
-        (void)o2;
       } else {
         // ---------------- dgrad conv (+ residual) fused with the CALayer backward of the block whose dL/dout it produces --------
         const int Cr = o.ca_cr;
@@ -1364,7 +915,7 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
             }
           }
         }
-        all_gather(et < 64 ? cta_total(et) : 0.f);        // (barriers: ca_z / ca_dv visible, S.ca_tot = sum g*t over the sample)
+        all_gather();                                     // (barriers: ca_z / ca_dv visible, S.ca_tot = sum g*t over the sample)
         if (et == 0) CL_TRACE(op, 14);
         if (et < 64) {
           float u = b2v;
@@ -1414,14 +965,11 @@ chain_cluster_kernel(const __grid_constant__ CMaps maps, const __grid_constant__
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const uint32_t gw[4] = {gv[g].x, gv[g].y, gv[g].z, gv[g].w};
-            float y8[8], d8[8];
-            load8(yh + g * 8, y8);
-            load8(dsh + g * 8, d8);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 fg = unpack_bf16x2(gw[e]);
               const int ch = g * 8 + e * 2;
-              pk[g * 4 + e] = pack_bf16x2(fmaf(fg.x, y8[e * 2], d8[e * 2]), fmaf(fg.y, y8[e * 2 + 1], d8[e * 2 + 1]));
+              pk[g * 4 + e] = pack_bf16x2(fmaf(fg.x, yh[ch], dsh[ch]), fmaf(fg.y, yh[ch + 1], dsh[ch + 1]));
               const float2 fd = unpack_bf16x2(pk[g * 4 + e]);
               rs[ch] += fd.x;
               rs[ch + 1] += fd.y;
@@ -1482,7 +1030,7 @@ int encode_5d(srb_ctx* ctx, CUtensorMap* map, void* ptr, int slots, int N, int H
 // CALayer-forward ops (which use the operand-tile buffer as staging) and TMA operand tiles (MASK / CA_BWD_FUSED) do not
 // occur in the same chain.  Returns 1 if it can run the chain, 0 if not (srb_conv_chain then uses the L2-flag kernel).
 int srb_chain_cluster_eligible(const srb_chain_desc* d) {
-  if (!cluster_enabled()) return 0;
+  if (!cluster_enabled() || d->kernel_hint == 1) return 0;
   if (d->H % 16 != 0 || (d->W != 24 && d->W != 48) || d->H < 16) return 0;
   const int bands = d->H / 16, halves = d->W / 24;
   if (bands * halves > kMaxCluster) return 0;
@@ -1606,30 +1154,6 @@ int srb_chain_cluster_launch(srb_ctx* ctx, const srb_chain_desc* d, void* stream
       } else {
         c.res_mode = RES_GLOBAL;
       }
-    }
-  }
-  // Sample-wide reductions off the critical path (SRB200_CLUSTER_CA_DEFER=0 keeps the two-pass forms):
-  //  * a plain conv followed by a CALayer op evaluates that op's gate from its own output's column sums (pre_pool / pooled);
-  //  * a CA_BWD_FUSED op followed by a plain conv publishes g*gate and lets the consumer add conv(ds/HW) (defer / field).
-  {
-    const char* e = getenv("SRB200_CLUSTER_CA_DEFER");
-    const bool on = !(e && e[0] == '0');
-    for (int i = 0; i < d->n_ops; ++i) p.ops[i].pre_pool = p.ops[i].pooled = p.ops[i].defer = p.ops[i].field = p.ops[i].skip_y = 0;
-    for (int i = 0; on && i + 1 < d->n_ops; ++i) {
-      const uint32_t f0 = d->ops[i].flags, f1 = d->ops[i + 1].flags;
-      const bool plain0 = !(f0 & (SRB_CHAIN_CA | SRB_CHAIN_CA_BWD_FUSED)), plain1 = !(f1 & (SRB_CHAIN_CA | SRB_CHAIN_CA_BWD_FUSED));
-      if (plain0 && (f1 & SRB_CHAIN_CA)) p.ops[i].pre_pool = p.ops[i + 1].pooled = 1;
-      if ((f0 & SRB_CHAIN_CA_BWD_FUSED) && plain1) p.ops[i].defer = p.ops[i + 1].field = 1;
-    }
-    for (int i = 0; i < d->n_ops; ++i) {
-      if (!p.ops[i].defer || !(d->ops[i].flags & SRB_CHAIN_Y_SCRATCH)) continue;
-      bool needed = false;
-      for (int k = i + 1; k < d->n_ops; ++k) {
-        const srb_chain_op& ok = d->ops[k];
-        if (ok.x == d->ops[i].y || ok.e2 == d->ops[i].y) needed = true;
-        if (ok.e == d->ops[i].y && !(k == i + 2 && p.ops[k].res_mode == RES_TMEM)) needed = true;
-      }
-      p.ops[i].skip_y = needed ? 0 : 1;
     }
   }
   SRB_REQUIRE(d->weights && d->n_layers > 0, "srb_conv_chain: conv ops need a filter bank");

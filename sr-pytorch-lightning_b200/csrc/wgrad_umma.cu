@@ -371,7 +371,10 @@ int srb_wgrad_umma_batched(srb_ctx* ctx, const srb_wgrad_desc* descs, const void
   if (total == 0) return 0;
   bool any_split = false;
   std::vector<int> launch_start;
-  plan_launches(blocks, ctx->num_sms, launch_start, any_split);
+  // a caller that runs these launches beside another kernel (the backward layer chain of the next ResidualGroup, which
+  // leaves SMs free) caps the grid so that both are resident at once
+  const int sm_cap = ctx->wgrad_sm_budget > 0 && ctx->wgrad_sm_budget < ctx->num_sms ? ctx->wgrad_sm_budget : ctx->num_sms;
+  plan_launches(blocks, sm_cap, launch_start, any_split);
   if (any_split) {
     // split reductions add into dW with red.global.add, so overwritten layers start from zero
     for (int i = 0; i < n_items; ++i)

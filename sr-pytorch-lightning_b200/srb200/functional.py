@@ -264,7 +264,7 @@ class RCANGroupFn(Function):
                        cw1.reshape(cw1.shape[0], 64), cb1, cw2.reshape(64, cw2.shape[1]), cb2, s_all[b], y_all[b])
             cur = ref(0, 3 * b + 2)
         ch.conv(cur, ref(0, 3 * nb), 2 * nb, params[-1].detach(), res=xin)
-        ch.run(bank)
+        ch.run(bank, hint=ops.chain_forward_hint())
         ctx.save_for_backward(x, A, s_all, y_all, *params)
         ctx.owner, ctx.nb = owner, nb
         return A[3 * nb]
@@ -313,12 +313,13 @@ class RCANGroupFn(Function):
             wq.append((A[3 * b - 1] if b > 0 else x, B[3 * b + 1], 8 * b, None))
             gref = ref(0, 3 * b + 2)
         ch.run(bank)
-        for xt, gy, wi, bi in wq:
-            wbuf, acc, grads[wi] = _grad_target(params[wi])
-            bbuf = None
-            if bi is not None:
-                bbuf, _, grads[bi] = _grad_target(params[bi])
-            ops.conv_wgrad(xt, 0, 64, gy, 0, 64, 3, wbuf, bbuf, accumulate=acc)
+        with ops.wgrad_overlap_section(bool(ch.used_cluster)):     # under the next group's backward chain if possible
+            for xt, gy, wi, bi in wq:
+                wbuf, acc, grads[wi] = _grad_target(params[wi])
+                bbuf = None
+                if bi is not None:
+                    bbuf, _, grads[bi] = _grad_target(params[bi])
+                ops.conv_wgrad(xt, 0, 64, gy, 0, 64, 3, wbuf, bbuf, accumulate=acc)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(g)

@@ -58,7 +58,7 @@ class ChainOp(C.Structure):
 class ChainDesc(C.Structure):
     _fields_ = [("N", c_i32), ("H", c_i32), ("W", c_i32), ("n_ops", c_i32), ("ops", C.POINTER(ChainOp)),
                 ("space_base", c_vp * 4), ("space_slots", c_i32 * 4), ("weights", c_vp), ("n_layers", c_i32),
-                ("counters", c_vp), ("trace", c_vp), ("tile_flags", c_vp)]
+                ("counters", c_vp), ("trace", c_vp), ("tile_flags", c_vp), ("kernel_hint", c_i32)]
 
 
 class HaloDesc(C.Structure):
@@ -84,6 +84,7 @@ PROTOTYPES = {
     "srb_conv": (c_i32, [c_vp, C.POINTER(ConvDesc)] + [c_vp] * 9),
     "srb_conv_wgrad": (c_i32, [c_vp, C.POINTER(WgradDesc)] + [c_vp] * 5),
     "srb_conv_wgrad_batched": (c_i32, [c_vp, C.POINTER(WgradItem), c_i32, c_vp]),
+    "srb_set_wgrad_sm_budget": (c_i32, [c_vp, c_i32]),
     "srb_conv_uses_umma": (c_i32, [C.POINTER(ConvDesc)]),
     "srb_wgrad_uses_umma": (c_i32, [C.POINTER(WgradDesc)]),
     "srb_wgrad_plan": (c_i32, [c_i32, c_i32] + [C.POINTER(c_i32)] * 5),

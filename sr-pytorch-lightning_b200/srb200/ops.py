@@ -308,6 +308,7 @@ class _WgradQueue:
         if not self.items:
             return
         items, self.items = self.items, []
+        self.flushed = items          # (WgradOverlap keeps these alive until the side stream has been joined)
         arr = (L.WgradItem * len(items))()
         for i, (d, x, gy, dw, dbias) in enumerate(items):
             arr[i].d = d
@@ -341,6 +342,100 @@ class deferred_wgrads:
         else:
             _wq.items = []
         return False
+
+
+class WgradOverlap:
+    """Weight gradients of a layer chain under the NEXT chain's backward launch.
+
+    The per-sample cluster chain kernel (conv_cluster.cu) occupies 6 SMs per sample — 96 of 148 for the 16-patch batch — and
+    is latency-bound; the batched weight-gradient kernel is throughput-bound and does not care which SMs it gets.  A chain's
+    backward function wraps its conv_wgrad calls in `section()`: the calls are collected and launched on a lower-priority
+    side stream right behind that chain's launch, with at most `sm_budget` CTAs (srb_set_wgrad_sm_budget), while the main
+    stream goes on with the next chain.  Only the first `max_sections` sections of a backward pass are overlapped — the side
+    stream falls behind (52 SMs do less than 148), and what it has not finished when the last chain ends would run on 52 SMs
+    only — the rest joins the ordinary deferred queue and runs on all SMs.  `join()` makes the main stream wait for the side
+    stream and drops the references that kept the operands alive.
+
+    Reference behaviour replaced: autograd runs each layer's weight gradient right behind its input gradient on the one
+    stream; the result is the same sum, accumulated into the same flat gradient buffer."""
+
+    def __init__(self, device, sm_budget: int = 52, max_sections: int = 8):
+        self.device = device
+        self.sm_budget = int(sm_budget)
+        self.max_sections = int(max_sections)
+        self.side = torch.cuda.Stream(device=device, priority=0)
+        self.keep = []
+        self.used = 0
+        self.sections_run = 0
+
+    def begin_pass(self):
+        self.used = 0
+
+    def take(self) -> bool:
+        if self.used >= self.max_sections:
+            return False
+        self.used += 1
+        return True
+
+    class _Section:
+        def __init__(self, ov):
+            self.ov = ov
+
+        def __enter__(self):
+            global _wq
+            self.saved = _wq
+            _wq = _WgradQueue()
+            _wq.active = True
+            _wq.max_items = 1 << 30
+            return self
+
+        def __exit__(self, *exc):
+            global _wq
+            q, _wq = _wq, self.saved
+            if exc[0] is not None or not q.items:
+                return False
+            ov = self.ov
+            main = torch.cuda.current_stream(ov.device)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            ov.side.wait_event(ev)
+            ov.keep.append(list(q.items))    # operands stay allocated until join(): the side stream still reads them
+            lib = L.load()
+            ctx = C.c_void_p(L.ctx(ov.device.index))
+            with torch.cuda.stream(ov.side):
+                L.check(lib.srb_set_wgrad_sm_budget(ctx, ov.sm_budget), "srb_set_wgrad_sm_budget")
+                try:
+                    q.flush()
+                finally:
+                    lib.srb_set_wgrad_sm_budget(ctx, 0)
+            ov.sections_run += 1
+            return False
+
+    def section(self):
+        return WgradOverlap._Section(self)
+
+    def join(self):
+        if self.keep:
+            torch.cuda.current_stream(self.device).wait_stream(self.side)
+            self.keep = []
+
+
+_overlap = None
+
+
+def set_wgrad_overlap(ov):
+    """Install (or clear, with None) the WgradOverlap the chain backward functions use."""
+    global _overlap
+    _overlap = ov
+
+
+def wgrad_overlap_section(used_cluster: bool):
+    """Context for the conv_wgrad calls of one chain: overlapped on the side stream if an overlap object is installed, the
+    chain ran as the cluster kernel (it leaves SMs free) and the pass has sections left; otherwise a no-op."""
+    import contextlib
+    if _overlap is not None and used_cluster and _wq.active and _overlap.take():
+        return _overlap.section()
+    return contextlib.nullcontext()
 
 
 def conv_wgrad(x, x_co, cin, gy, g_co, cout, k, dw, dbias, *, accumulate=False, shuffle=0, alpha=1.0,
@@ -483,6 +578,15 @@ class FilterBank:
         return bank
 
 
+def chain_forward_hint() -> int:
+    """Kernel for FORWARD chains (srb_chain_desc.kernel_hint).  Nothing else runs beside a forward chain, so the L2-flag
+    kernel, which spreads the tiles over all SMs, is the faster one there (RCAN ResidualGroup on [16,48,48,64]: 271 us
+    against 279 us); backward chains take the cluster kernel, whose free SMs run the weight gradients (WgradOverlap).
+    SRB200_CHAIN_FWD=cluster|flags overrides."""
+    import os
+    return 0 if os.environ.get("SRB200_CHAIN_FWD", "flags") == "cluster" else 1
+
+
 def chain_tile_flags() -> bool:
     """Layers of a chain are ordered with per-tile flags: a tile waits for the 3x3 neighbourhood of tiles of
     the previous op instead of for the slowest of its sample's tiles (RCAN step 8.25 -> 7.94 ms).
@@ -582,7 +686,7 @@ class Chain:
         o.colsum = self._ptr(colsum_dt)
         return o
 
-    def run(self, bank: torch.Tensor | None, trace: torch.Tensor | None = None):
+    def run(self, bank: torch.Tensor | None, trace: torch.Tensor | None = None, hint: int = 0):
         """Launch; more than CHAIN_MAX_OPS ops are split into consecutive launches (stream order
         carries the dependency across the split)."""
         lib = L.load()
@@ -611,6 +715,7 @@ class Chain:
             if trace is None:
                 trace = CHAIN_TRACE
             d.trace = trace.data_ptr() if trace is not None else None
+            d.kernel_hint = hint
             self.used_cluster = bool(lib.srb_conv_chain_uses_cluster(C.byref(d)))
             L.check(lib.srb_conv_chain(C.c_void_p(L.ctx(self.device.index)), C.byref(d), _stream()), "srb_conv_chain")
 

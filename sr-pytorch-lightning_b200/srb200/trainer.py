@@ -108,6 +108,17 @@ class TrainStep:
         self.launches_per_step = 0
         self.arena = ops.ZeroArena(dev)
         self.pack_table = None
+        # weight gradients of a ResidualGroup under the next group's backward chain (ops.WgradOverlap): needs the cluster
+        # chain kernel, which leaves 52 of the 148 SMs free.  SRB200_WGRAD_OVERLAP=0 turns it off;
+        # SRB200_WGRAD_OVERLAP_SMS / _GROUPS set the CTA budget of the overlapped launches / how many groups overlap.
+        import os
+        self.overlap = None
+        if dev.type == "cuda" and os.environ.get("SRB200_WGRAD_OVERLAP", "1") not in ("", "0") \
+                and os.environ.get("SRB200_CHAIN_CLUSTER", "1") not in ("0",) \
+                and os.environ.get("SRB200_NO_CHAIN", "0") in ("", "0"):
+            self.overlap = ops.WgradOverlap(dev, sm_budget=int(os.environ.get("SRB200_WGRAD_OVERLAP_SMS", "52")),
+                                            max_sections=int(os.environ.get("SRB200_WGRAD_OVERLAP_GROUPS", "8")))
+        self.main = torch.cuda.Stream(device=dev, priority=-1) if dev.type == "cuda" else None     # the step's own (higher-priority) stream
         self.sync_from_rank0()
 
     def sync_from_rank0(self):
@@ -132,8 +143,16 @@ class TrainStep:
             loss = F200.l1_loss(sr, self.hr)
             # weight gradients batched, off the dgrad chain; ONE flush for the whole step, so that the launch planner
             # (wgrad_umma.cu plan_launches) sees every layer and leaves at most one partially filled launch
-            with ops.deferred_wgrads(max_items=4096):
-                loss.backward()
+            ops.set_wgrad_overlap(self.overlap)
+            if self.overlap is not None:
+                self.overlap.begin_pass()
+            try:
+                with ops.deferred_wgrads(max_items=4096):
+                    loss.backward()
+                if self.overlap is not None:
+                    self.overlap.join()
+            finally:
+                ops.set_wgrad_overlap(None)
             if self.world > 1:
                 dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.pg)
             ops.inc_counter(self.flat.step_dev)
@@ -147,7 +166,7 @@ class TrainStep:
         """Warm-up steps (sizes the arena, fills the packed-weight caches), then build the pack
         table and, if enabled, capture the step into a CUDA graph."""
         from . import lib as L
-        side = torch.cuda.Stream(device=self.device)
+        side = self.main
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(max(2, warmup)):
@@ -161,7 +180,7 @@ class TrainStep:
             return
         c0 = L.launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=self.main):
             self._body()
         self.launches_per_step = L.launch_count() - c0
         torch.cuda.synchronize()
