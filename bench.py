@@ -428,7 +428,7 @@ def run_infer4k(dev, world, rank, local, peaks, min_seconds: float, with_cpu: bo
     import torch.distributed as dist
     import models
     from srb200 import lib as L
-    from srb200.tiled import DistExchange, TiledEDSR, partition_rows
+    from srb200.tiled import DistExchange, PeerExchange, TiledEDSR, partition_rows
     H, W, S = 540, 960, 4
     torch.manual_seed(0)
     m = models.EDSR(n_feats=256, n_resblocks=32, res_scale=0.1, scale_factor=S)
@@ -437,13 +437,24 @@ def run_infer4k(dev, world, rank, local, peaks, min_seconds: float, with_cpu: bo
     g = torch.Generator().manual_seed(0)
     host_x = [torch.rand(1, 3, H, W, generator=g).pin_memory() for _ in range(2)]
     dev_x = [t.to(dev) for t in host_x]
+    peer = None
     if world > 1:
-        runner = TiledEDSR(m, DistExchange())
         r0, r1 = partition_rows(H, world)[rank]
         out_rows = (r1 - r0) * S
+        if os.environ.get("SRB200_TILED_EXCHANGE", "peer") == "peer":
+            # halo rows by peer stores over NVLink from one kernel per layer, the strip forward replayed as one CUDA graph
+            peer = PeerExchange(device=dev)
+            runner = TiledEDSR(m, peer)
+            with torch.no_grad():
+                runner.prepare(dev_x[0], use_graph=True)
 
-        def fn(x):
-            return runner.forward(x)[rank].clamp_(0, 1)
+            def fn(x):
+                return runner.run(x)[rank].clamp_(0, 1)
+        else:
+            runner = TiledEDSR(m, DistExchange())
+
+            def fn(x):
+                return runner.forward(x)[rank].clamp_(0, 1)
     else:
         out_rows = H * S
 
@@ -487,6 +498,8 @@ def run_infer4k(dev, world, rank, local, peaks, min_seconds: float, with_cpu: bo
         barrier()
         ms_total = max_over_ranks(e0.elapsed_time(e1))
         launches = L.launch_count() - c0
+        if peer is not None and runner.graph is not None:
+            launches = runner.launches_per_frame * frames      # graph replays do not pass through the host-side counter
         # end to end: pinned host frame in, pinned host SR frame (this rank's strip) out, every frame
         xin = torch.empty_like(dev_x[0])
         frames_e = max(5, frames // 2)
@@ -503,6 +516,8 @@ def run_infer4k(dev, world, rank, local, peaks, min_seconds: float, with_cpu: bo
         barrier()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
         clocks = sampler.stop() if sampler is not None else None
+    if peer is not None:
+        peer.close()
     if rank != 0:
         return None
     gflop_frame = 231.5644 * (H * W) / (48 * 48)
@@ -512,7 +527,10 @@ def run_infer4k(dev, world, rank, local, peaks, min_seconds: float, with_cpu: bo
         "frames": frames, "seconds": ms_total / 1e3, "ms_per_frame": ms, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "EDSR(n_feats=256, n_resblocks=32, res_scale=0.1, scale_factor=4) predict path (forward + clamp) on "
                                "torch.rand(1,3,540,960) (BASELINE.json configs[4])",
-                   "parallelism": "single GPU, whole frame" if world == 1 else f"{world} row strips, per-layer halo exchange (srb200/tiled.py)",
+                   "parallelism": "single GPU, whole frame" if world == 1 else
+                   (f"{world} row strips; per layer ONE kernel pushes the border rows into the neighbours' halo rows through NVLink peer "
+                    f"memory and synchronises by flags (csrc/halo.cu); strip forward = one CUDA graph" if peer is not None else
+                    f"{world} row strips, per-layer NCCL send/recv halo exchange (srb200/tiled.py DistExchange)"),
                    "l2": "activations of one layer (265 MB bf16) exceed the 126 MB L2; 2 input frames rotate"},
         "tflops_algorithmic": gflop_frame / ms / world, "frac_of_burst_peak_per_gpu": gflop_frame / ms / world / peaks["burst"],
         "frac_of_sustained_peak_per_gpu": gflop_frame / ms / world / peaks["sustained"],

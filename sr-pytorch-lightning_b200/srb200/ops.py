@@ -359,8 +359,11 @@ class WgradOverlap:
     Reference behaviour replaced: autograd runs each layer's weight gradient right behind its input gradient on the one
     stream; the result is the same sum, accumulated into the same flat gradient buffer."""
 
-    def __init__(self, device, sm_budget: int = 52, max_sections: int = 8):
+    def __init__(self, device, sm_budget: int = 52, max_sections: int = 8, on_section_done=None):
         self.device = device
+        # on_section_done(lo_ptr, hi_ptr): called on the side stream behind a section's launches with the address range of the
+        # gradient buffers they wrote (data-parallel training: all-reduce that bucket under the following chains)
+        self.on_section_done = on_section_done
         self.sm_budget = int(sm_budget)
         self.max_sections = int(max_sections)
         self.side = torch.cuda.Stream(device=device, priority=0)
@@ -408,6 +411,12 @@ class WgradOverlap:
                     q.flush()
                 finally:
                     lib.srb_set_wgrad_sm_budget(ctx, 0)
+                if ov.on_section_done is not None:
+                    lo = min(min(it[3].data_ptr(), it[4].data_ptr() if it[4] is not None else it[3].data_ptr()) for it in ov.keep[-1])
+                    hi = max(max(it[3].data_ptr() + it[3].numel() * it[3].element_size(),
+                                 (it[4].data_ptr() + it[4].numel() * it[4].element_size()) if it[4] is not None else 0)
+                             for it in ov.keep[-1])
+                    ov.on_section_done(lo, hi)
             ov.sections_run += 1
             return False
 

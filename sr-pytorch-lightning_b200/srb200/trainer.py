@@ -117,7 +117,12 @@ class TrainStep:
                 and os.environ.get("SRB200_CHAIN_CLUSTER", "1") not in ("0",) \
                 and os.environ.get("SRB200_NO_CHAIN", "0") in ("", "0"):
             self.overlap = ops.WgradOverlap(dev, sm_budget=int(os.environ.get("SRB200_WGRAD_OVERLAP_SMS", "52")),
-                                            max_sections=int(os.environ.get("SRB200_WGRAD_OVERLAP_GROUPS", "8")))
+                                            max_sections=int(os.environ.get("SRB200_WGRAD_OVERLAP_GROUPS", "8")),
+                                            on_section_done=self._reduce_bucket if self.world > 1 and
+                                            os.environ.get("SRB200_ALLREDUCE_BUCKETS", "0") not in ("", "0") else None)
+        self._reduced = []          # [lo, hi) element ranges of flat.grad already all-reduced in this step
+        self._pending = None        # (lo, hi, groups) collected for the next bucket
+        self._bucket_groups = int(os.environ.get("SRB200_ALLREDUCE_BUCKET_GROUPS", "2"))
         self.main = torch.cuda.Stream(device=dev, priority=-1) if dev.type == "cuda" else None     # the step's own (higher-priority) stream
         self.sync_from_rank0()
 
@@ -128,6 +133,44 @@ class TrainStep:
             src = dist.get_global_rank(self.pg, 0) if self.pg is not None else 0
             for t in (self.flat.flat, self.flat.m, self.flat.v, self.flat.step_dev):
                 dist.broadcast(t, src=src, group=self.pg)
+
+    def _reduce_bucket(self, lo_ptr: int, hi_ptr: int):
+        """All-reduce the slice of the flat gradient buffer a ResidualGroup's backward has completed (called on the
+        weight-gradient side stream right behind that group's launches): the bucket travels over NVLink under the following
+        groups' backward chains, as Lightning DDP's buckets do for the reference (configs/all.yml:125-127)."""
+        base = self.flat.grad.data_ptr()
+        lo = max(0, (lo_ptr - base) // 4)
+        hi = min(self.flat.numel, (hi_ptr - base + 3) // 4)
+        if hi <= lo:
+            return
+        # Several groups per bucket: the all-reduce sits on the weight-gradient stream, which is as long as the chain stream
+        # beside it; one launch per group (8 x ~50 us) made the step LONGER at N=2 (7.71 -> 7.88 ms), fewer and larger ones
+        # amortise the launch latency.  Consecutive groups are adjacent parameter ranges, so a bucket stays one slice.
+        if self._pending and (self._pending[1] == lo or self._pending[0] == hi):
+            self._pending = (min(lo, self._pending[0]), max(hi, self._pending[1]), self._pending[2] + 1)
+        else:
+            self._flush_bucket()
+            self._pending = (lo, hi, 1)
+        if self._pending[2] >= self._bucket_groups:
+            self._flush_bucket()
+
+    def _flush_bucket(self):
+        if self._pending:
+            lo, hi, _ = self._pending
+            dist.all_reduce(self.flat.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+            self._reduced.append((lo, hi))
+        self._pending = None
+
+    def _reduce_rest(self):
+        """All-reduce what no bucket covered (head, up-sampling, tail, the groups whose weight gradients ran last)."""
+        if self._pending:            # (a partial bucket: reduce it with the rest, on this stream)
+            self._pending = None
+        cur = 0
+        for lo, hi in sorted(self._reduced) + [(self.flat.numel, self.flat.numel)]:
+            if lo > cur:
+                dist.all_reduce(self.flat.grad[cur:lo], op=dist.ReduceOp.SUM, group=self.pg)
+            cur = max(cur, hi)
+        self._reduced = []
 
     # the work of one step; captured once
     def _body(self):
@@ -154,7 +197,7 @@ class TrainStep:
             finally:
                 ops.set_wgrad_overlap(None)
             if self.world > 1:
-                dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.pg)
+                self._reduce_rest()
             ops.inc_counter(self.flat.step_dev)
             ops.adam_step(self.flat.flat, self.flat.grad, self.flat.m, self.flat.v, step=0,
                           step_dev=self.flat.step_dev, grad_scale=1.0 / self.world, **self.hp)

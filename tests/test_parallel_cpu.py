@@ -97,3 +97,45 @@ def test_dist_exchange_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True, True), (1, True, True)]
+
+
+def _bucket_worker(rank, world, port, q):
+    """TrainStep's bucket bookkeeping with real gloo all-reduces on a CPU flat buffer: buckets reduced early (as the
+    weight-gradient side stream does per ResidualGroup) + _reduce_rest for the complement = one all-reduce of the whole
+    buffer, every element exactly once."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from srb200.trainer import TrainStep
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.Conv2d(8, 8, 3), torch.nn.Conv2d(8, 5, 3), torch.nn.Conv2d(5, 3, 1))
+        ts = TrainStep(net, (2, 3, 8, 8), 1)
+        ts._bucket_groups = 1
+        assert ts.world == world
+        n = ts.flat.numel
+        ts.flat.grad.copy_(torch.arange(n, dtype=torch.float32) * (rank + 1))
+        base = ts.flat.grad.data_ptr()
+        # two disjoint buckets in "backward order" with unaligned edges; the complement is three separate ranges
+        o = ts.flat.offsets
+        ts._reduce_bucket(base + 4 * o[4], base + 4 * n)
+        ts._reduce_bucket(base + 4 * (o[2] + 1), base + 4 * (o[4] - 3))
+        covered = list(ts._reduced)
+        ts._reduce_rest()
+        want = torch.arange(n, dtype=torch.float32) * sum(range(1, world + 1))
+        q.put((rank, covered == [(o[4], n), (o[2] + 1, o[4] - 3)], bool(torch.equal(ts.flat.grad, want)), ts._reduced == []))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_buckets_cover_the_flat_buffer_exactly_once_gloo_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True, True, True), (1, True, True, True)]
