@@ -29,6 +29,7 @@ for i in range(steps):
 print(f"rank {os.environ.get('RANK', 0)} losses", " ".join(f"{v:.6f}" for v in out))
 gn = float(ts.flat.grad.double().norm())
 print(f"grad norm {gn:.6e}  overlap sections {ts.overlap.sections_run if ts.overlap else 0}")
-if "LOCAL_RANK" in os.environ:
-    import torch.distributed as dist
-    dist.destroy_process_group()
+if "LOCAL_RANK" in os.environ:      # (tearing NCCL down under a live CUDA graph can hang: leave at once)
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0)

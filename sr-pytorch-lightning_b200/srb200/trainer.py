@@ -122,7 +122,14 @@ class TrainStep:
                                             os.environ.get("SRB200_ALLREDUCE_BUCKETS", "0") not in ("", "0") else None)
         self._reduced = []          # [lo, hi) element ranges of flat.grad already all-reduced in this step
         self._pending = None        # (lo, hi, groups) collected for the next bucket
-        self._bucket_groups = int(os.environ.get("SRB200_ALLREDUCE_BUCKET_GROUPS", "2"))
+        # SRB200_ALLREDUCE_BUCKETS: "0" (default) = one all-reduce of the whole buffer after backward; "tail" = the gradients of the groups whose weight gradients ran on the side
+        # stream are all-reduced as ONE bucket on that stream once it has finished, i.e. under the weight-gradient launches
+        # that are left for the main stream (which then leave SRB200_ALLREDUCE_SMS SMs to NCCL); "1" = a bucket every
+        # SRB200_ALLREDUCE_BUCKET_GROUPS groups during backward (measured slower: the side stream is already as long as the
+        # chain stream).  Measured at N=2: 7.66 ms ("0"), 7.71 ("tail"), 7.75 ("1", 2 groups), 7.88 ("1", 1 group).
+        self._bucket_mode = os.environ.get("SRB200_ALLREDUCE_BUCKETS", "0")
+        self._bucket_groups = (1 << 30) if self._bucket_mode == "tail" else int(os.environ.get("SRB200_ALLREDUCE_BUCKET_GROUPS", "2"))
+        self._nccl_sms = int(os.environ.get("SRB200_ALLREDUCE_SMS", "16"))
         self.main = torch.cuda.Stream(device=dev, priority=-1) if dev.type == "cuda" else None     # the step's own (higher-priority) stream
         self.sync_from_rank0()
 
@@ -189,9 +196,23 @@ class TrainStep:
             ops.set_wgrad_overlap(self.overlap)
             if self.overlap is not None:
                 self.overlap.begin_pass()
+            tail_bucket = self.world > 1 and self.overlap is not None and self.overlap.on_section_done is not None \
+                and self._bucket_mode == "tail"
             try:
-                with ops.deferred_wgrads(max_items=4096):
-                    loss.backward()
+                from . import lib as L
+                import ctypes as C
+                ctx = C.c_void_p(L.ctx(self.device.index)) if tail_bucket else None
+                try:
+                    with ops.deferred_wgrads(max_items=4096):
+                        loss.backward()
+                        if tail_bucket and self._pending:
+                            with torch.cuda.stream(self.overlap.side):
+                                self._flush_bucket()          # behind the side stream's last weight-gradient launch
+                            # the launches flushed on leaving this block share the GPU with that all-reduce
+                            L.load().srb_set_wgrad_sm_budget(ctx, max(1, L.load().srb_num_sms(ctx) - self._nccl_sms))
+                finally:
+                    if tail_bucket:
+                        L.load().srb_set_wgrad_sm_budget(ctx, 0)
                 if self.overlap is not None:
                     self.overlap.join()
             finally:
