@@ -397,13 +397,18 @@ def roofline_for(model_key: str, dev, peaks, ms_step):
         us = 0.5 * (k["us_f"] + k["us_b"])
         tf = k["flop"] / (us * 1e-6) / 1e12
         per_step = 20 if model_key == "rcan" else 2
+        fwd_cluster = k["cluster"] and os.environ.get("SRB200_CHAIN_FWD", "flags") == "cluster"
         key = "chain_cluster" if k["cluster"] else "chain_flags"
         what = ("one RCAN ResidualGroup (20 RCAB + conv = 41 tcgen05 3x3 64->64 convs, CALayer fused)" if model_key == "rcan"
                 else "the EDSR body (16 ResBlocks + conv = 33 tcgen05 3x3 64->64 convs)")
+        kern = ("conv_chain_kernel (L2 tile flags, 144 CTAs)" if not k["cluster"] else
+                "chain_cluster_kernel (conv_cluster.cu: one 6-CTA thread-block cluster per sample, 96 CTAs)" if fwd_cluster else
+                "forward launch conv_chain_kernel (conv_chain.cu: L2 tile flags, 144 CTAs), backward launch chain_cluster_kernel "
+                "(conv_cluster.cu: one 6-CTA cluster per sample, 96 CTAs; the other 52 SMs run the previous group's weight gradients "
+                "in the step)")
         return {"bound": "tensor", "achieved": tf, "peak": peaks["burst"], "unit": "TFLOP/s", "frac": tf / peaks["burst"],
                 "traffic": TRAFFIC.get(key),
-                "kernel": f"{'chain_cluster_kernel (conv_cluster.cu: one thread-block cluster per sample)' if k['cluster'] else 'conv_chain_kernel'}: "
-                          f"{what} per launch on [16,48,48,64] bf16; average of the forward and the backward launch, timed alone "
+                "kernel": f"{kern}: {what} per launch on [16,48,48,64] bf16; average of the forward and the backward launch, timed alone "
                           f"over graph replays of 10 rotating arena sets (2.9 GB > L2)",
                 "us_per_launch": us, "us_forward_launch": k["us_f"], "us_backward_launch": k["us_b"], "flop_per_launch": k["flop"],
                 "launches_per_step": per_step,
@@ -700,11 +705,16 @@ def run_ours(args):
         c0 = L.launch_count()
         barrier()
         torch.cuda.synchronize()
+        ncu_range = os.environ.get("SRB200_NCU_RANGE", "0") not in ("", "0")      # `ncu --profile-from-start off`: timed region only
+        if ncu_range:
+            torch.cuda.profiler.start()
         e0.record()
         for i in range(args.steps):
             step.step(dev_lr[i % nb], dev_hr[i % nb])
         e1.record()
         torch.cuda.synchronize()
+        if ncu_range:
+            torch.cuda.profiler.stop()
         barrier()
         ms_total = max_over_ranks(e0.elapsed_time(e1))
         launches = step.launches_per_step * args.steps if step.graph is not None else L.launch_count() - c0
@@ -748,7 +758,11 @@ def run_ours(args):
         chain_note = ""
         if args.model in ("rcan", "edsr"):
             off = os.environ.get("SRB200_NO_CHAIN", "0") not in ("", "0")
-            chain_note = ("; 64-channel trunks run as layer-chain launches (srb_conv_chain: per-sample cluster kernel)"
+            ov = getattr(step, "overlap", None)
+            chain_note = ("; 64-channel trunks run as layer-chain launches (srb_conv_chain: forward = L2-flag kernel on all SMs, "
+                          "backward = per-sample cluster kernel on 96 SMs"
+                          + (f" with the previous group's weight gradients on <= {ov.sm_budget} CTAs of a side stream "
+                             f"({ov.max_sections} groups)" if ov is not None else "") + ")"
                           + (" [disabled]" if off else ""))
         line = {
             "metric": metric_name(args.model), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

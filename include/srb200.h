@@ -135,12 +135,16 @@ typedef struct srb_wgrad_item {
   float* dw;
   float* dbias;             /* may be NULL */
 } srb_wgrad_item;
+/* an item with dw == NULL and dbias != NULL is a bias gradient only (column sums of gy; x is ignored) */
 int  srb_conv_wgrad_batched(srb_ctx*, const srb_wgrad_item* items, int n, void* stream);
 /* max_ctas > 0: the batched weight-gradient launches of later srb_conv_wgrad_batched calls use at most that many CTAs
  * (one per SM), so that they fit beside a kernel that leaves SMs free — the per-sample cluster chain (96 of 148 SMs for
  * 16 x 48x48) on another stream; 0 restores "all SMs".  Replaces nothing in the reference: torch runs the weight
  * gradients of a layer right behind its input gradient on the same stream (autograd engine). */
 int  srb_set_wgrad_sm_budget(srb_ctx*, int max_ctas);
+/* a one-thread kernel that occupies the stream for ns nanoseconds (<= 1 ms): lets a kernel on ANOTHER stream that becomes
+ * runnable at the same moment reach the SMs first (the cluster chain before the weight gradients that run beside it) */
+int  srb_delay(srb_ctx*, int64_t ns, void* stream);
 /* which kernel family (and hence which weight packing) backend AUTO resolves to */
 int  srb_conv_uses_umma(const srb_conv_desc*);
 int  srb_wgrad_uses_umma(const srb_wgrad_desc*);

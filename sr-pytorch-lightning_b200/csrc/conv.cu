@@ -101,6 +101,25 @@ extern "C" int srb_conv_wgrad_batched(srb_ctx* ctx, const srb_wgrad_item* items,
   std::vector<float> calpha;
   for (int i = 0; i < n; ++i) {
     const srb_wgrad_item& it = items[i];
+    if (it.gy && it.dbias && !it.dw) {      // bias gradient only (its weight gradient ran elsewhere): column sums of gy
+      const int64_t npix = (int64_t)it.d.N * it.d.H * it.d.W;
+      if (batch_colsums && srb_colsum_batched_ok(it.gy, it.d.g_cs, it.d.g_co, it.d.Cout, it.d.dtype)) {
+        cx.push_back(it.gy);
+        ccs.push_back(it.d.g_cs);
+        cco.push_back(it.d.g_co);
+        cC.push_back(it.d.Cout);
+        cnp.push_back(npix);
+        cout_.push_back(it.dbias);
+        cacc.push_back(it.d.accumulate);
+        calpha.push_back(it.d.alpha);
+        cshuf.push_back(it.d.shuffle);
+      } else {
+        int rc = srb_colsum_launch(ctx, it.gy, it.d.g_cs, it.d.g_co, it.d.Cout, npix, it.d.dtype, it.dbias, it.d.accumulate,
+                                   it.d.alpha, it.d.shuffle, st);
+        if (rc) return rc;
+      }
+      continue;
+    }
     SRB_REQUIRE(it.x && it.gy && it.dw, "srb_conv_wgrad_batched: item %d has a null pointer", i);
     const bool umma = it.d.backend != SRB_BACKEND_SIMT && srb_wgrad_umma_ok(&it.d);
     if (umma) {

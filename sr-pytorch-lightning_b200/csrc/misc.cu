@@ -682,3 +682,27 @@ extern "C" int srb_pack_table(srb_ctx* ctx, const srb_pack_item* table_dev, int 
   SRB_LAUNCH_CHECK();
   return 0;
 }
+
+// ---- stream delay ---------------------------------------------------------------------------------------------------
+// One thread that waits `ns` nanoseconds.  Used at the head of the weight-gradient side stream (srb200.ops.WgradOverlap):
+// the batched weight-gradient launch and the next backward chain both become runnable when the previous chain ends, and
+// the chain's cluster launch reaches the SMs ~1.5 us later; if the weight-gradient CTAs are placed first they are spread
+// over all GPCs and the 16 six-SM clusters no longer fit at once (chain launch 345 -> 580 us).
+__global__ void delay_kernel(unsigned long long ns) {
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (true) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 >= ns) break;
+    __nanosleep(100);
+  }
+}
+
+extern "C" int srb_delay(srb_ctx* ctx, int64_t ns, void* stream) {
+  SRB_REQUIRE(ctx && ns >= 0 && ns <= 1000000, "srb_delay: 0 <= ns <= 1e6");
+  if (ns == 0) return 0;
+  delay_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>((unsigned long long)ns);
+  SRB_LAUNCH_CHECK();
+  return 0;
+}

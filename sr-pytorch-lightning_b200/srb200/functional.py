@@ -313,13 +313,20 @@ class RCANGroupFn(Function):
             wq.append((A[3 * b - 1] if b > 0 else x, B[3 * b + 1], 8 * b, None))
             gref = ref(0, 3 * b + 2)
         ch.run(bank)
-        with ops.wgrad_overlap_section(bool(ch.used_cluster)):     # under the next group's backward chain if possible
+        ops.wgrad_overlap_kick()      # the previous group's weight gradients start BEHIND this launch, on the SMs it leaves free
+        late_bias = []
+        with ops.wgrad_overlap_section(bool(ch.used_cluster)) as sec:     # under the next group's backward chain if possible
             for xt, gy, wi, bi in wq:
                 wbuf, acc, grads[wi] = _grad_target(params[wi])
                 bbuf = None
                 if bi is not None:
                     bbuf, _, grads[bi] = _grad_target(params[bi])
+                    if sec is not None:       # a column-sum launch per group would sit on the side stream's critical path:
+                        late_bias.append((gy, bbuf, acc))     # leave the bias to the step's one batched column-sum launch
+                        bbuf = None
                 ops.conv_wgrad(xt, 0, 64, gy, 0, 64, 3, wbuf, bbuf, accumulate=acc)
+        for gy, bbuf, acc in late_bias:
+            ops.bias_grad(gy, 0, 64, bbuf, accumulate=acc)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(g)

@@ -85,6 +85,7 @@ PROTOTYPES = {
     "srb_conv_wgrad": (c_i32, [c_vp, C.POINTER(WgradDesc)] + [c_vp] * 5),
     "srb_conv_wgrad_batched": (c_i32, [c_vp, C.POINTER(WgradItem), c_i32, c_vp]),
     "srb_set_wgrad_sm_budget": (c_i32, [c_vp, c_i32]),
+    "srb_delay": (c_i32, [c_vp, c_i64, c_vp]),
     "srb_conv_uses_umma": (c_i32, [C.POINTER(ConvDesc)]),
     "srb_wgrad_uses_umma": (c_i32, [C.POINTER(WgradDesc)]),
     "srb_wgrad_plan": (c_i32, [c_i32, c_i32] + [C.POINTER(c_i32)] * 5),

@@ -314,7 +314,7 @@ class _WgradQueue:
             arr[i].d = d
             arr[i].x = x.data_ptr()
             arr[i].gy = gy.data_ptr()
-            arr[i].dw = dw.data_ptr()
+            arr[i].dw = dw.data_ptr() if dw is not None else None
             arr[i].dbias = dbias.data_ptr() if dbias is not None else None
         L.check(L.load().srb_conv_wgrad_batched(_ctx(items[0][1]), arr, len(items), _stream()), "srb_conv_wgrad_batched")
 
@@ -368,6 +368,9 @@ class WgradOverlap:
         self.max_sections = int(max_sections)
         self.side = torch.cuda.Stream(device=device, priority=0)
         self.keep = []
+        self.pending = None          # (queue, event) of the last section, launched by kick()
+        import os
+        self.head_delay_ns = int(os.environ.get("SRB200_WGRAD_OVERLAP_DELAY_NS", "8000"))
         self.used = 0
         self.sections_run = 0
 
@@ -398,32 +401,46 @@ class WgradOverlap:
             if exc[0] is not None or not q.items:
                 return False
             ov = self.ov
-            main = torch.cuda.current_stream(ov.device)
+            ov.kick()                        # (an earlier section nobody kicked)
             ev = torch.cuda.Event()
-            ev.record(main)
-            ov.side.wait_event(ev)
+            ev.record(torch.cuda.current_stream(ov.device))
             ov.keep.append(list(q.items))    # operands stay allocated until join(): the side stream still reads them
-            lib = L.load()
-            ctx = C.c_void_p(L.ctx(ov.device.index))
-            with torch.cuda.stream(ov.side):
-                L.check(lib.srb_set_wgrad_sm_budget(ctx, ov.sm_budget), "srb_set_wgrad_sm_budget")
-                try:
-                    q.flush()
-                finally:
-                    lib.srb_set_wgrad_sm_budget(ctx, 0)
-                if ov.on_section_done is not None:
-                    lo = min(min(it[3].data_ptr(), it[4].data_ptr() if it[4] is not None else it[3].data_ptr()) for it in ov.keep[-1])
-                    hi = max(max(it[3].data_ptr() + it[3].numel() * it[3].element_size(),
-                                 (it[4].data_ptr() + it[4].numel() * it[4].element_size()) if it[4] is not None else 0)
-                             for it in ov.keep[-1])
-                    ov.on_section_done(lo, hi)
-            ov.sections_run += 1
+            ov.pending = (q, ev)
             return False
 
     def section(self):
         return WgradOverlap._Section(self)
 
+    def kick(self):
+        """Launch the pending section on the side stream.  Called right AFTER the next chain has been enqueued on the main
+        stream: both only wait for the previous chain, and whichever reaches the GPU first takes its SMs first — the
+        weight-gradient CTAs, spread over all GPCs, once left the cluster kernel without room for all 16 of its 6-SM
+        clusters until they had finished (chain launch 375 -> 580 us, profiles/r02_step_timeline_v2_race.txt)."""
+        if self.pending is None:
+            return
+        (q, ev), self.pending = self.pending, None
+        self.side.wait_event(ev)
+        lib = L.load()
+        ctx = C.c_void_p(L.ctx(self.device.index))
+        with torch.cuda.stream(self.side):
+            if self.head_delay_ns > 0:       # let the chain launch that became runnable at the same instant take its SMs first
+                L.check(lib.srb_delay(ctx, self.head_delay_ns, _stream()), "srb_delay")
+            L.check(lib.srb_set_wgrad_sm_budget(ctx, self.sm_budget), "srb_set_wgrad_sm_budget")
+            try:
+                q.flush()
+            finally:
+                lib.srb_set_wgrad_sm_budget(ctx, 0)
+            if self.on_section_done is not None:
+                items = q.flushed
+                lo = min(min(it[3].data_ptr(), it[4].data_ptr() if it[4] is not None else it[3].data_ptr()) for it in items)
+                hi = max(max(it[3].data_ptr() + it[3].numel() * it[3].element_size(),
+                             (it[4].data_ptr() + it[4].numel() * it[4].element_size()) if it[4] is not None else 0)
+                         for it in items)
+                self.on_section_done(lo, hi)
+        self.sections_run += 1
+
     def join(self):
+        self.kick()
         if self.keep:
             torch.cuda.current_stream(self.device).wait_stream(self.side)
             self.keep = []
@@ -438,6 +455,12 @@ def set_wgrad_overlap(ov):
     _overlap = ov
 
 
+def wgrad_overlap_kick():
+    """To be called right after a chain launch: starts the previous chain's weight gradients beside it."""
+    if _overlap is not None:
+        _overlap.kick()
+
+
 def wgrad_overlap_section(used_cluster: bool):
     """Context for the conv_wgrad calls of one chain: overlapped on the side stream if an overlap object is installed, the
     chain ran as the cluster kernel (it leaves SMs free) and the pass has sections left; otherwise a no-op."""
@@ -445,6 +468,27 @@ def wgrad_overlap_section(used_cluster: bool):
     if _overlap is not None and used_cluster and _wq.active and _overlap.take():
         return _overlap.section()
     return contextlib.nullcontext()
+
+
+def bias_grad(gy, g_co, cout, dbias, *, accumulate=False, alpha=1.0):
+    """dbias (+)= alpha * per-channel sums of gy, as a deferred item when a queue is active (it then shares the batch's one
+    column-sum launch), else at once."""
+    if not _wq.active:
+        assert alpha == 1.0
+        colsum(gy, g_co, cout, dbias, accumulate=accumulate)
+        return
+    n, h, w, gcs = _nhwc(gy)
+    d = L.WgradDesc()
+    d.N, d.H, d.W = n, h, w
+    d.Cin, d.Cout, d.ksize = cout, cout, 1
+    d.dtype = dtype_code(gy)
+    d.accumulate = 1 if accumulate else 0
+    d.shuffle = 0
+    d.backend = L.BACKEND_AUTO
+    d.x_cs, d.x_co = gcs, g_co
+    d.g_cs, d.g_co = gcs, g_co
+    d.alpha = float(alpha)
+    _wq.push(d, gy, gy, None, dbias)
 
 
 def conv_wgrad(x, x_co, cin, gy, g_co, cout, k, dw, dbias, *, accumulate=False, shuffle=0, alpha=1.0,
