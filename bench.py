@@ -366,8 +366,18 @@ def time_chain_kernel(dev, model_key: str, reps=10):
             for x, g in zip(xs, gs):
                 call(x).backward(g)
                 q.items.clear()
-    us_f = _graph_time(wrap(fwd), reps)
-    us_fb = _graph_time(wrap(fwd_bwd), reps)
+    # the backward launch is timed in the form the training step uses: RCAN = cluster kernel (weight gradients run beside it
+    # there), EDSR (a single chain) = L2-flag kernel
+    cluster_on = os.environ.get("SRB200_CHAIN_CLUSTER", "1") not in ("0",) and os.environ.get("SRB200_WGRAD_OVERLAP", "1") not in ("", "0")
+    saved_bwd = os.environ.get("SRB200_CHAIN_BWD")
+    if model_key == "rcan" and cluster_on and saved_bwd is None:
+        os.environ["SRB200_CHAIN_BWD"] = "cluster"
+    try:
+        us_f = _graph_time(wrap(fwd), reps)
+        us_fb = _graph_time(wrap(fwd_bwd), reps)
+    finally:
+        if saved_bwd is None:
+            os.environ.pop("SRB200_CHAIN_BWD", None)
     flat.detach()
     flop = n_convs * 2.0 * BATCH * LR * LR * 64 * 64 * 9
     cluster = os.environ.get("SRB200_CHAIN_CLUSTER", "1") not in ("0",) and os.environ.get("SRB200_NO_CHAIN", "0") in ("", "0")
@@ -401,7 +411,7 @@ def roofline_for(model_key: str, dev, peaks, ms_step):
         key = "chain_cluster" if k["cluster"] else "chain_flags"
         what = ("one RCAN ResidualGroup (20 RCAB + conv = 41 tcgen05 3x3 64->64 convs, CALayer fused)" if model_key == "rcan"
                 else "the EDSR body (16 ResBlocks + conv = 33 tcgen05 3x3 64->64 convs)")
-        kern = ("conv_chain_kernel (L2 tile flags, 144 CTAs)" if not k["cluster"] else
+        kern = ("conv_chain_kernel (L2 tile flags, 144 CTAs)" if (not k["cluster"] or model_key == "edsr") else
                 "chain_cluster_kernel (conv_cluster.cu: one 6-CTA thread-block cluster per sample, 96 CTAs)" if fwd_cluster else
                 "forward launch conv_chain_kernel (conv_chain.cu: L2 tile flags, 144 CTAs), backward launch chain_cluster_kernel "
                 "(conv_cluster.cu: one 6-CTA cluster per sample, 96 CTAs; the other 52 SMs run the previous group's weight gradients "

@@ -318,11 +318,6 @@ int  srb_ipc_open(srb_ctx*, const unsigned char handle[64], void** ptr);
 int  srb_ipc_close(srb_ctx*, void* ptr);
 int  srb_ipc_free(srb_ctx*, void* ptr);
 
-/* ---- diagnostics (not on the product path) -------------------------------------------------
- * tcgen05.mma throughput probe: `blocks` CTAs each issue `iters` MMAs 128 x N x 16 (bf16, SS,
- * 128-B swizzle; mn_major selects the operand major-ness) and write their elapsed SM cycles. */
-int  srb_probe_umma(srb_ctx*, int N, int iters, int mn_major, int distinct, int blocks,
-                    long long* cycles_dev, void* stream);
 
 /* per-CTA event clocks of the 3x3 64-channel conv kernel (16 int64 per CTA; NULL = off) */
 int  srb_debug_set_trace(srb_ctx*, long long* dev_buf);

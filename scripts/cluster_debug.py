@@ -302,6 +302,8 @@ def stage_model(name, n=2):
     for mode in ("cluster", "flags", "layers"):
         os.environ["SRB200_NO_CHAIN"] = "1" if mode == "layers" else "0"
         os.environ["SRB200_CHAIN_CLUSTER"] = "1" if mode == "cluster" else "0"
+        os.environ["SRB200_CHAIN_FWD"] = "cluster" if mode == "cluster" else "flags"      # (the defaults pick per direction)
+        os.environ["SRB200_CHAIN_BWD"] = "cluster" if mode == "cluster" else "flags"
         m = cls(**kw)
         m.load_state_dict(sd)
         m.compute_dtype = "bf16"

@@ -312,7 +312,8 @@ class RCANGroupFn(Function):
             wq.append((A[3 * b], B[3 * b], 8 * b + 2, None))
             wq.append((A[3 * b - 1] if b > 0 else x, B[3 * b + 1], 8 * b, None))
             gref = ref(0, 3 * b + 2)
-        ch.run(bank)
+        # the cluster kernel (96 SMs) only pays when weight gradients run beside it; alone, the L2-flag kernel is faster
+        ch.run(bank, hint=ops.chain_backward_hint())
         ops.wgrad_overlap_kick()      # the previous group's weight gradients start BEHIND this launch, on the SMs it leaves free
         late_bias = []
         with ops.wgrad_overlap_section(bool(ch.used_cluster)) as sec:     # under the next group's backward chain if possible
@@ -363,7 +364,7 @@ class ResTrunkFn(Function):
             ch.conv(ref(0, 2 * b), ref(0, 2 * b + 1), 2 * b + 1, b2, scale=scale, res=cur)
             cur = ref(0, 2 * b + 1)
         ch.conv(cur, ref(0, 2 * nb), 2 * nb, params[-1].detach(), res=xin)
-        ch.run(bank)
+        ch.run(bank, hint=ops.chain_forward_hint())
         ctx.save_for_backward(x, A, *params)
         ctx.owner, ctx.nb, ctx.scale = owner, nb, scale
         return A[2 * nb]
@@ -403,7 +404,8 @@ class ResTrunkFn(Function):
             wq.append((A[2 * b], B[gslot], 4 * b + 2, None, scale))
             wq.append((A[2 * b - 1] if b > 0 else x, B[2 * b], 4 * b, None, 1.0))
             gslot = 2 * b + 1
-        ch.run(bank)
+        # a single chain: nothing to run beside it, the L2-flag kernel on all SMs is faster (SRB200_CHAIN_BWD=cluster overrides)
+        ch.run(bank, hint=0 if __import__("os").environ.get("SRB200_CHAIN_BWD") == "cluster" else 1)
         for xt, gy, wi, bi, alpha in wq:
             wbuf, acc, grads[wi] = _grad_target(params[wi])
             bbuf = None

@@ -111,7 +111,6 @@ PROTOTYPES = {
     "srb_ipc_open": (c_i32, [c_vp, C.c_char_p, C.POINTER(c_vp)]),
     "srb_ipc_close": (c_i32, [c_vp, c_vp]),
     "srb_ipc_free": (c_i32, [c_vp, c_vp]),
-    "srb_probe_umma": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "srb_debug_set_trace": (c_i32, [c_vp, c_vp]),
 }
 

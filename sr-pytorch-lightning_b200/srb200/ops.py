@@ -455,6 +455,10 @@ def set_wgrad_overlap(ov):
     _overlap = ov
 
 
+def wgrad_overlap_installed() -> bool:
+    return _overlap is not None and _wq.active
+
+
 def wgrad_overlap_kick():
     """To be called right after a chain launch: starts the previous chain's weight gradients beside it."""
     if _overlap is not None:
@@ -638,6 +642,18 @@ def chain_forward_hint() -> int:
     SRB200_CHAIN_FWD=cluster|flags overrides."""
     import os
     return 0 if os.environ.get("SRB200_CHAIN_FWD", "flags") == "cluster" else 1
+
+
+def chain_backward_hint() -> int:
+    """Kernel for BACKWARD chains of a multi-chain model (RCAN): the cluster kernel when weight gradients run beside it
+    (WgradOverlap installed, i.e. inside TrainStep), else the L2-flag kernel.  SRB200_CHAIN_BWD=cluster|flags overrides."""
+    import os
+    e = os.environ.get("SRB200_CHAIN_BWD", "auto")
+    if e == "cluster":
+        return 0
+    if e == "flags":
+        return 1
+    return 0 if wgrad_overlap_installed() else 1
 
 
 def chain_tile_flags() -> bool:

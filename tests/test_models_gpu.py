@@ -25,11 +25,11 @@ TOL = {"fp32": 1e-4, "bf16": 2e-2}           # north_star bars: outputs (and los
 # fixtures, shows global 4e-3..1.8e-2, worst single tensor 1.1e-1, input gradient 4.8e-2..6.8e-2
 # (measured in the build container, DESIGN.md "Parity").
 GLOBAL_GRAD_TOL = {"fp32": 1e-4, "bf16": 2e-2}
-PER_PARAM_TOL = {"fp32": 1e-3, "bf16": 1.5e-1}
+PER_PARAM_TOL = {"fp32": 1e-3, "bf16": 6e-2}      # measured worst: 8.1e-4 / 4.6e-2 (profiles/r02_parity_report.jsonl)
 # The input-image gradient is not a north_star quantity (parameters are what training uses); it has
 # crossed >400 bf16 layers in the 200-block RCAN and sits at 7e-2..9e-2 run to run (atomics order),
 # next to 6.8e-2 for the reference's own autocast run.
-INPUT_GRAD_TOL = {"fp32": 1e-3, "bf16": 1.2e-1}
+INPUT_GRAD_TOL = {"fp32": 1e-3, "bf16": 1.0e-1}     # measured worst: 2.1e-4 / 8.1e-2
 
 REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_report.jsonl")
 
