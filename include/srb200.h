@@ -319,6 +319,24 @@ int  srb_ipc_close(srb_ctx*, void* ptr);
 int  srb_ipc_free(srb_ctx*, void* ptr);
 
 
+/* ---- GPU data path for training batches (replaces the per-sample PIL work of the reference's
+ * srdata.py:57-169 `_get_item` / `_get_patch`: aligned random LR / HR crop, rotation by a multiple of 90 degrees, flips,
+ * TF.to_tensor) for uint8 HWC RGB images resident in device memory.  The host draws the random choices (as the reference
+ * does, from Python's `random`) and uploads n items; one launch writes lr_out [n][3][p][p] and hr_out [n][3][p*s][p*s]
+ * (fp32, values k/255).  Order of operations and edge behaviour as the reference: crop (zero where the box leaves the
+ * image), rotate counter-clockwise, hflip, vflip.  Either output may be NULL. */
+typedef struct srb_patch_item {
+  const uint8_t* lr_img;    /* [lr_h][lr_w][3] */
+  const uint8_t* hr_img;    /* [hr_h][hr_w][3] */
+  int32_t lr_h, lr_w, hr_h, hr_w;
+  int32_t lr_top, lr_left;  /* crop origin in the LR image; the HR origin is scale times it */
+  int32_t angle;            /* 0, 90, 180, 270 */
+  int32_t hflip, vflip;
+  int32_t reserved;
+} srb_patch_item;
+int  srb_patch_batch(srb_ctx*, const srb_patch_item* items_dev, int n, int lr_patch, int scale, float* lr_out, float* hr_out,
+                     void* stream);
+
 /* per-CTA event clocks of the 3x3 64-channel conv kernel (16 int64 per CTA; NULL = off) */
 int  srb_debug_set_trace(srb_ctx*, long long* dev_buf);
 

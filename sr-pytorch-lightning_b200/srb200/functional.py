@@ -312,6 +312,8 @@ class RCANGroupFn(Function):
             wq.append((A[3 * b], B[3 * b], 8 * b + 2, None))
             wq.append((A[3 * b - 1] if b > 0 else x, B[3 * b + 1], 8 * b, None))
             gref = ref(0, 3 * b + 2)
+        if ops.chain_backward_hint() == 0:
+            ops.wgrad_overlap_adopt()     # (first group of the pass only) what is already queued runs beside this chain
         # the cluster kernel (96 SMs) only pays when weight gradients run beside it; alone, the L2-flag kernel is faster
         ch.run(bank, hint=ops.chain_backward_hint())
         ops.wgrad_overlap_kick()      # the previous group's weight gradients start BEHIND this launch, on the SMs it leaves free

@@ -34,6 +34,11 @@ class WgradDesc(C.Structure):
                                      "backend", "x_cs", "x_co", "g_cs", "g_co")] + [("alpha", c_f32)]
 
 
+class PatchItem(C.Structure):
+    _fields_ = [("lr_img", c_vp), ("hr_img", c_vp)] + [(n, c_i32) for n in ("lr_h", "lr_w", "hr_h", "hr_w", "lr_top", "lr_left",
+                                                                           "angle", "hflip", "vflip", "reserved")]
+
+
 class PackItem(C.Structure):
     _fields_ = [("src", c_vp), ("dst", c_vp)] + [(n, c_i32) for n in ("Cout", "Cin", "ksize", "packing", "mode", "shuffle")]
 
@@ -86,6 +91,7 @@ PROTOTYPES = {
     "srb_conv_wgrad_batched": (c_i32, [c_vp, C.POINTER(WgradItem), c_i32, c_vp]),
     "srb_set_wgrad_sm_budget": (c_i32, [c_vp, c_i32]),
     "srb_delay": (c_i32, [c_vp, c_i64, c_vp]),
+    "srb_patch_batch": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "srb_conv_uses_umma": (c_i32, [C.POINTER(ConvDesc)]),
     "srb_wgrad_uses_umma": (c_i32, [C.POINTER(WgradDesc)]),
     "srb_wgrad_plan": (c_i32, [c_i32, c_i32] + [C.POINTER(c_i32)] * 5),

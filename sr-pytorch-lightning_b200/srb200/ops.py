@@ -369,6 +369,7 @@ class WgradOverlap:
         self.side = torch.cuda.Stream(device=device, priority=0)
         self.keep = []
         self.pending = None          # (queue, event) of the last section, launched by kick()
+        self.adopted = False         # the layers behind the trunk have been taken over in this pass (wgrad_overlap_adopt)
         import os
         self.head_delay_ns = int(os.environ.get("SRB200_WGRAD_OVERLAP_DELAY_NS", "8000"))
         self.used = 0
@@ -376,6 +377,7 @@ class WgradOverlap:
 
     def begin_pass(self):
         self.used = 0
+        self.adopted = False
 
     def take(self) -> bool:
         if self.used >= self.max_sections:
@@ -457,6 +459,22 @@ def set_wgrad_overlap(ov):
 
 def wgrad_overlap_installed() -> bool:
     return _overlap is not None and _wq.active
+
+
+def wgrad_overlap_adopt():
+    """Before the FIRST backward chain of a pass: the weight gradients queued so far (tail, up-sampling convs — the layers
+    behind the trunk, whose backward has just run) become a side-stream section of their own, so that they run beside that
+    first chain, which otherwise has nothing beside it, instead of after the last one."""
+    ov = _overlap
+    if ov is None or not _wq.active or ov.adopted or not _wq.items or ov.pending is not None:
+        return
+    ov.adopted = True
+    q = _WgradQueue()
+    q.items, _wq.items = _wq.items, []
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(ov.device))
+    ov.keep.append(list(q.items))
+    ov.pending = (q, ev)
 
 
 def wgrad_overlap_kick():
