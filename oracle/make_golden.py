@@ -37,6 +37,8 @@ CASES = {
     "rdn_b_x4":       ("RDN", dict(rdn_config="B", scale_factor=4), (1, 3, 16, 16), 0.577),
     "rdn_a_x2":       ("RDN", dict(rdn_config="A", scale_factor=2), (1, 3, 16, 16), 0.577),
     "srcnn_x2":       ("SRCNN", dict(scale_factor=2), (2, 3, 16, 16), 0.577),
+    "wdsr_b_x4":      ("WDSR", dict(type="B", n_feats=64, n_resblocks=3, res_scale=1, scale_factor=4), (2, 3, 16, 24), 0.577),
+    "wdsr_a_x2":      ("WDSR", dict(type="A", n_feats=32, n_resblocks=2, res_scale=1, scale_factor=2), (1, 3, 16, 16), 0.577),
 }
 
 FULL_GRAD_MAX_ELEMS = 40_000

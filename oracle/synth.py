@@ -51,7 +51,9 @@ def synth_state_dict(shapes: dict[str, tuple], seed: int = 0, gain: float = 1.0,
         if frozen is not None and name in frozen:
             out[name] = np.asarray(frozen[name], dtype=np.float32).reshape(shp)
             continue
-        if len(shp) == 4:
+        if name.endswith("weight_g"):        # weight-norm gains (wdsr.py:65): the filter's norm itself, keep it O(1) and positive
+            out[name] = synth_tensor(shp, name, seed, 0.5 * gain, 1.5 * gain)
+        elif len(shp) == 4:
             fan_in = shp[1] * shp[2] * shp[3]
             b = gain * math.sqrt(3.0 / fan_in)
             out[name] = synth_tensor(shp, name, seed, -b, b)

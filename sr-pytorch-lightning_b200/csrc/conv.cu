@@ -30,7 +30,7 @@ static int check_conv_desc(const srb_conv_desc* d, const void* x, const void* w,
   SRB_REQUIRE(d->x_co + d->Cin <= d->x_cs, "srb_conv: input channel slice [%d,%d) exceeds stride %d", d->x_co,
               d->x_co + d->Cin, d->x_cs);
   const int rr = d->shuffle > 1 ? d->shuffle * d->shuffle : 1;
-  SRB_REQUIRE(d->shuffle == 0 || d->shuffle == 2 || d->shuffle == 3, "srb_conv: shuffle must be 0, 2 or 3");
+  SRB_REQUIRE(d->shuffle == 0 || (d->shuffle >= 2 && d->shuffle <= 8), "srb_conv: shuffle must be 0 or 2..8");
   SRB_REQUIRE(d->Cout % rr == 0, "srb_conv: Cout %d not divisible by r^2=%d", d->Cout, rr);
   SRB_REQUIRE(d->y_co + d->Cout / rr <= d->y_cs, "srb_conv: output channel slice exceeds stride");
   SRB_REQUIRE(!(d->flags & SRB_RESIDUAL) || res, "srb_conv: RESIDUAL without residual pointer");

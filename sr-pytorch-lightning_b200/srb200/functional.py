@@ -104,16 +104,20 @@ class ConvFn(Function):
             gm = torch.empty_like(g)
             ops.relu_bwd(g, 0, y, 0, gm, 0, cout)
         if shuffle > 1:
-            gm = ops.pixel_unshuffle(gm, shuffle)   # [N,H,W,Cout] in (ij, c') channel order
+            gm = ops.pixel_unshuffle(gm, shuffle, cout // (shuffle * shuffle))   # [N,H,W,Cout] in (ij, c') channel order
         dw = db = dx = None
         if ctx.needs_input_grad[1]:
             wbuf, wacc, dw = _grad_target(weight)
+            bbuf = None
             if bias is not None and ctx.needs_input_grad[2]:
                 bbuf, bacc, db = _grad_target(bias)
-                assert bacc == wacc
-            else:
-                bbuf = None
-            ops.conv_wgrad(x, 0, cin, gm, 0, cout, k, wbuf, bbuf, accumulate=wacc, shuffle=shuffle, alpha=scale)
+                if bacc != wacc:
+                    # the weight is a derived tensor (weight-norm: its gradient goes back to autograd in a fresh buffer) while the
+                    # bias lives in the flat gradient buffer: the two targets accumulate differently, so the bias gets its own item
+                    ops.bias_grad(gm, 0, cout, bbuf, accumulate=bacc, alpha=scale, shuffle=shuffle)
+                    bbuf = None
+            # a gradient handed back to autograd (dw is not None) must exist when this function returns
+            ops.conv_wgrad(x, 0, cin, gm, 0, cout, k, wbuf, bbuf, accumulate=wacc, shuffle=shuffle, alpha=scale, defer=dw is None)
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             if shuffle > 1:

@@ -492,30 +492,33 @@ def wgrad_overlap_section(used_cluster: bool):
     return contextlib.nullcontext()
 
 
-def bias_grad(gy, g_co, cout, dbias, *, accumulate=False, alpha=1.0):
-    """dbias (+)= alpha * per-channel sums of gy, as a deferred item when a queue is active (it then shares the batch's one
-    column-sum launch), else at once."""
-    if not _wq.active:
-        assert alpha == 1.0
-        colsum(gy, g_co, cout, dbias, accumulate=accumulate)
-        return
+def bias_grad(gy, g_co, cout, dbias, *, accumulate=False, alpha=1.0, shuffle=0):
+    """dbias (+)= alpha * per-channel sums of gy (`shuffle` > 1: gy's channels are in (sub-pixel, c') order, dbias in the
+    parameter's), as a deferred item when a queue is active (it then shares the batch's one column-sum launch), else at once."""
     n, h, w, gcs = _nhwc(gy)
     d = L.WgradDesc()
     d.N, d.H, d.W = n, h, w
     d.Cin, d.Cout, d.ksize = cout, cout, 1
     d.dtype = dtype_code(gy)
     d.accumulate = 1 if accumulate else 0
-    d.shuffle = 0
+    d.shuffle = shuffle
     d.backend = L.BACKEND_AUTO
     d.x_cs, d.x_co = gcs, g_co
     d.g_cs, d.g_co = gcs, g_co
     d.alpha = float(alpha)
-    _wq.push(d, gy, gy, None, dbias)
+    if _wq.active:
+        _wq.push(d, gy, gy, None, dbias)
+        return
+    arr = (L.WgradItem * 1)()
+    arr[0].d, arr[0].x, arr[0].gy, arr[0].dw, arr[0].dbias = d, gy.data_ptr(), gy.data_ptr(), None, dbias.data_ptr()
+    L.check(L.load().srb_conv_wgrad_batched(_ctx(gy), arr, 1, _stream()), "srb_conv_wgrad_batched")
 
 
 def conv_wgrad(x, x_co, cin, gy, g_co, cout, k, dw, dbias, *, accumulate=False, shuffle=0, alpha=1.0,
-               backend=L.BACKEND_AUTO):
-    """dw (fp32 OIHW) (+)= alpha * correlation(x, gy); dbias (+)= alpha * sum(gy)."""
+               backend=L.BACKEND_AUTO, defer=True):
+    """dw (fp32 OIHW) (+)= alpha * correlation(x, gy); dbias (+)= alpha * sum(gy).
+    defer=False: launch now even inside `deferred_wgrads()` — for a gradient that autograd goes on to consume (the filter
+    of a weight-normalised conv is a derived tensor: its gradient feeds the g / v backward right away)."""
     lib = L.load()
     n, h, w, xcs = _nhwc(x)
     d = L.WgradDesc()
@@ -528,7 +531,7 @@ def conv_wgrad(x, x_co, cin, gy, g_co, cout, k, dw, dbias, *, accumulate=False, 
     d.x_cs, d.x_co = xcs, x_co
     d.g_cs, d.g_co = gy.shape[3], g_co
     d.alpha = float(alpha)
-    if _wq.active:
+    if _wq.active and defer:
         _wq.push(d, x, gy, dw, dbias)
         return
     L.check(lib.srb_conv_wgrad(_ctx(x), C.byref(d), _p(x), _p(gy), _p(dw), _p(dbias), _stream()), "srb_conv_wgrad")
@@ -593,11 +596,17 @@ def relu_bwd(g, g_co, act, a_co, out, o_co, c):
                                   o_co, c, npix, dtype_code(g), _stream()), "srb_relu_bwd")
 
 
-def pixel_unshuffle(g, r):
-    n, hr, wr, cp = _nhwc(g)
+def pixel_unshuffle(g, r, cp=None):
+    """cp: logical channels of g (default: all of them); g may be wider (bf16 tensors keep pixels 16-byte aligned, so the
+    3-channel output of WDSR's shuffled tail / skip convs is stored 8 wide)."""
+    n, hr, wr, gcs = _nhwc(g)
+    cp = gcs if cp is None else cp
     h, w = hr // r, wr // r
-    out = torch.empty((n, h, w, cp * r * r), dtype=g.dtype, device=g.device)
-    L.check(L.load().srb_pixel_unshuffle(_ctx(g), _p(g), cp, 0, _p(out), cp * r * r, 0, n, h, w, cp, r, dtype_code(g),
+    ocs = cp * r * r
+    if g.dtype == torch.bfloat16 and ocs % 8:
+        ocs = (ocs + 7) // 8 * 8
+    out = torch.empty((n, h, w, ocs), dtype=g.dtype, device=g.device)
+    L.check(L.load().srb_pixel_unshuffle(_ctx(g), _p(g), gcs, 0, _p(out), ocs, 0, n, h, w, cp, r, dtype_code(g),
                                          _stream()), "srb_pixel_unshuffle")
     return out
 

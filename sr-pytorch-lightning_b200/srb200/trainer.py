@@ -59,6 +59,14 @@ class FlatParams:
         for p in self.params:
             p._srb_grad_live = zero
 
+    def collect_autograd_grads(self):
+        """Parameters whose gradient torch autograd produced itself (weight-norm's g and v: the kernels only see the derived
+        filter) have it in `.grad`: move it into the flat buffer the fused Adam reads."""
+        for p in self.params:
+            if p.grad is not None:
+                p._srb_grad.add_(p.grad)
+                p.grad = None
+
     def grads_by_name(self, model):
         return {k: p._srb_grad for k, p in model.named_parameters() if p.requires_grad}
 
@@ -215,6 +223,7 @@ class TrainStep:
                         L.load().srb_set_wgrad_sm_budget(ctx, 0)
                 if self.overlap is not None:
                     self.overlap.join()
+                self.flat.collect_autograd_grads()
             finally:
                 ops.set_wgrad_overlap(None)
             if self.world > 1:

@@ -35,6 +35,8 @@ def test_state_dict_layout_matches_golden(name):
     ("RCAN", dict(n_feats=64, n_resblocks=20, n_resgroups=10, reduction=16, scale_factor=4)),
     ("RDN", dict(rdn_config="B", scale_factor=3)),
     ("SRCNN", dict(scale_factor=3)),
+    ("WDSR", dict(type="B", n_feats=128, n_resblocks=16, scale_factor=4)),
+    ("WDSR", dict(type="A", n_feats=32, n_resblocks=3, scale_factor=2)),
 ])
 def test_state_dict_layout_matches_reference(cls, kw):
     import models
@@ -56,12 +58,13 @@ def test_state_dict_layout_matches_reference(cls, kw):
 def test_registry_and_signatures():
     import inspect
     import models
-    assert set(models.__all__) == {"EDSR", "RCAN", "RDN", "SRCNN", "SRModel"}
-    for cls in ("EDSR", "RCAN", "RDN", "SRCNN"):
+    assert set(models.__all__) == {"EDSR", "RCAN", "RDN", "SRCNN", "SRModel", "WDSR"}
+    for cls in ("EDSR", "RCAN", "RDN", "SRCNN", "WDSR"):
         assert issubclass(getattr(models, cls), models.SRModel)
     assert list(inspect.signature(models.EDSR.__init__).parameters)[1:4] == ["n_feats", "n_resblocks", "res_scale"]
     assert list(inspect.signature(models.RCAN.__init__).parameters)[1:6] == ["n_feats", "n_resblocks", "n_resgroups", "reduction", "res_scale"]
     assert list(inspect.signature(models.RDN.__init__).parameters)[1:4] == ["rdn_config", "G0", "kernel_size"]
+    assert list(inspect.signature(models.WDSR.__init__).parameters)[1:5] == ["type", "n_feats", "n_resblocks", "res_scale"]      # wdsr.py:59
     m = models.RCAN()
     assert len(m.body) == 11 and len(m.body[0].body) == 17        # reference defaults (rcan.py:82)
     assert "compute_dtype" not in m.hparams and m.hparams["scale_factor"] == 4
@@ -99,7 +102,8 @@ def test_product_path_has_no_cpu_fallback(monkeypatch):
     at load time (never a silent PyTorch/oracle fallback)."""
     import models
     from srb200 import lib
-    for cls, kw in (("EDSR", dict(n_resblocks=1)), ("RCAN", dict(n_resblocks=1, n_resgroups=1)), ("RDN", {}), ("SRCNN", dict(scale_factor=2))):
+    for cls, kw in (("EDSR", dict(n_resblocks=1)), ("RCAN", dict(n_resblocks=1, n_resgroups=1)), ("RDN", {}), ("SRCNN", dict(scale_factor=2)),
+                    ("WDSR", dict(n_feats=16, n_resblocks=1))):
         m = getattr(models, cls)(**kw)
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             m(torch.rand(1, 3, 8, 8))

@@ -10,6 +10,7 @@ CASES = [
     ("RCAN", dict(n_feats=64, n_resblocks=2, n_resgroups=2, reduction=16, scale_factor=4)),
     ("EDSR", dict(n_feats=64, n_resblocks=3, res_scale=0.5, scale_factor=2)),
     ("RDN", dict(rdn_config="B", scale_factor=2)),
+    ("WDSR", dict(type="B", n_feats=64, n_resblocks=2, scale_factor=2)),     # weight-norm: g / v gradients come from autograd
 ]
 
 
@@ -19,7 +20,7 @@ def _batches(n, s, steps, seed=0):
 
 
 @pytest.mark.parametrize("use_graph", [False, True])
-@pytest.mark.parametrize("cls,kwargs", CASES[:2])
+@pytest.mark.parametrize("cls,kwargs", CASES[:2] + CASES[3:])
 def test_trainstep_matches_autograd_adam_bf16(cls, kwargs, use_graph):
     import models
     from srb200.trainer import TrainStep
@@ -95,6 +96,8 @@ def test_trainstep_fp32_matches_oracle_adam(cls, kwargs):
         cfg.update(n_resblocks=kwargs["n_resblocks"], n_resgroups=kwargs["n_resgroups"])
     elif cls == "EDSR":
         cfg.update(n_resblocks=kwargs["n_resblocks"], res_scale=kwargs["res_scale"])
+    elif cls == "WDSR":
+        cfg.update(type=kwargs["type"], n_feats=kwargs["n_feats"], n_resblocks=kwargs["n_resblocks"])
     else:
         cfg.update(rdn_config=kwargs["rdn_config"])
     ref_losses = []
