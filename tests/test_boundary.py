@@ -186,7 +186,7 @@ def test_integration_option_b_registry_snippet_runs(tmp_path):
         "models_b200 = importlib.util.module_from_spec(_spec)\n"
         "sys.modules['models_b200'] = models_b200\n"
         "_spec.loader.exec_module(models_b200)\n"
-        "from models_b200 import EDSR, RCAN, RDN, SRCNN, SRModel\n")
+        "from models_b200 import EDSR, RCAN, RDN, SRCNN, WDSR, SRModel\n")
     out = _run("import models; m = models.EDSR(n_resblocks=1); assert issubclass(models.EDSR, models.SRModel); "
                "print('OK', type(m).__module__, len(m.state_dict()))", cwd=str(tmp_path))
     assert "OK models_b200.edsr" in out
