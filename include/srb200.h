@@ -319,6 +319,26 @@ int  srb_ipc_close(srb_ctx*, void* ptr);
 int  srb_ipc_free(srb_ctx*, void* ptr);
 
 
+/* ---- BatchNorm2d + PReLU for the SRResNet family (reference models/srresnet.py:9-36 over
+ * common.py:33-55,74-109 with norm=nn.BatchNorm2d(n_feats), act=nn.PReLU()).  NHWC, 16-byte channel vectors: C, strides and
+ * offsets multiples of 8 (bf16) / 4 (fp32).
+ * srb_bn_stats: batch statistics over npix pixels (two passes: mean, then squared deviations): mean[C], rstd[C] =
+ *   1/sqrt(biased var + eps); running_mean / running_var (nullable) updated as torch does (momentum, unbiased variance).
+ *   ws: 2*C floats of scratch.
+ * srb_bn_act_fwd: y = PReLU_a((x - mean) * rstd * gamma + beta) + res; the four BN vectors are given together or all NULL
+ *   (no normalisation), prelu_a (one fp32 slope) and res are optional.
+ * srb_bn_act_bwd: g = dL/dy -> dx (the residual's gradient is g itself); dgamma / dbeta [C] and da [1] are written, or
+ *   added to if accumulate != 0.  ws: 3*C floats of scratch. */
+int  srb_bn_stats(srb_ctx*, const void* x, int x_cs, int x_co, int C, int64_t npix, int dtype, float eps, float momentum,
+                  float* ws, float* mean, float* rstd, float* running_mean, float* running_var, void* stream);
+int  srb_bn_act_fwd(srb_ctx*, const void* x, int x_cs, int x_co, int C, int64_t npix, int dtype, const float* mean,
+                    const float* rstd, const float* gamma, const float* beta, const float* prelu_a, const void* res, int r_cs,
+                    int r_co, void* y, int y_cs, int y_co, void* stream);
+int  srb_bn_act_bwd(srb_ctx*, const void* g, int g_cs, int g_co, const void* x, int x_cs, int x_co, int C, int64_t npix,
+                    int dtype, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                    const float* prelu_a, float* ws, void* dx, int dx_cs, int dx_co, float* dgamma, float* dbeta, float* da,
+                    int accumulate, void* stream);
+
 /* ---- GPU data path for training batches (replaces the per-sample PIL work of the reference's
  * srdata.py:57-169 `_get_item` / `_get_patch`: aligned random LR / HR crop, rotation by a multiple of 90 degrees, flips,
  * TF.to_tensor) for uint8 HWC RGB images resident in device memory.  The host draws the random choices (as the reference

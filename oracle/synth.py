@@ -51,7 +51,15 @@ def synth_state_dict(shapes: dict[str, tuple], seed: int = 0, gain: float = 1.0,
         if frozen is not None and name in frozen:
             out[name] = np.asarray(frozen[name], dtype=np.float32).reshape(shp)
             continue
-        if name.endswith("weight_g"):        # weight-norm gains (wdsr.py:65): the filter's norm itself, keep it O(1) and positive
+        if name.endswith("num_batches_tracked"):
+            out[name] = np.zeros(shp, dtype=np.int64)
+        elif name.endswith("running_var"):
+            out[name] = synth_tensor(shp, name, seed, 0.5, 1.5)
+        elif name.endswith("running_mean"):
+            out[name] = synth_tensor(shp, name, seed, -0.1, 0.1)
+        elif name.endswith(".weight") and len(shp) == 1:        # PReLU slope (one element) / BatchNorm gamma
+            out[name] = synth_tensor(shp, name, seed, 0.1, 0.4) if shp == (1,) else synth_tensor(shp, name, seed, 0.5, 1.5)
+        elif name.endswith("weight_g"):        # weight-norm gains (wdsr.py:65): the filter's norm itself, keep it O(1) and positive
             out[name] = synth_tensor(shp, name, seed, 0.5 * gain, 1.5 * gain)
         elif len(shp) == 4:
             fan_in = shp[1] * shp[2] * shp[3]

@@ -1,4 +1,4 @@
-"""Per-parameter gradient errors of WDSR golden cases against the oracle (debugging aid)."""
+"""Per-parameter gradient errors of a golden case against the oracle (debugging aid): python scripts/wdsr_debug.py <case> <fp32|bf16>"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "sr-pytorch-lightning_b200")); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))

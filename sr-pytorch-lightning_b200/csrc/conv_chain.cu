@@ -1044,7 +1044,19 @@ extern "C" int srb_conv_chain(srb_ctx* ctx, const srb_chain_desc* d, void* strea
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = reinterpret_cast<cudaStream_t>(stream);
-  cfg.numAttrs = 0;
+  // The CTAs spin-wait on each other's tile flags, so ALL of them must be resident at once.  grid <= #SMs with one CTA per SM
+  // makes that true on an idle GPU, but not beside another stream's kernel (weight gradients, NCCL) or under MPS / a profiler:
+  // a cooperative launch makes the driver hold the kernel back until the whole grid fits instead of letting the waits run into
+  // their 2 s bound.  SRB200_CHAIN_COOP=0 launches plainly (A/B timing).
+  static const bool coop = [] {
+    const char* e = getenv("SRB200_CHAIN_COOP");
+    return !(e && e[0] == '0');
+  }();
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = coop ? 1 : 0;
   SRB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_chain_kernel, maps, p));
   SRB_LAUNCH_CHECK();
   return 0;

@@ -512,6 +512,56 @@ class ConcatConv1x1Fn(Function):
         return (dw, db, None, *outs)
 
 
+class BnActFn(Function):
+    """y = PReLU_a( BatchNorm(x) ) + residual on NHWC tensors — each of the three optional — as one element-wise launch
+    (+ two statistics launches in training mode): the conv -> norm -> act chains of the reference's BasicBlock / ResBlock
+    (common.py:33-55,74-109) as SRResNet builds them (srresnet.py:13-30).  Training mode normalises with the batch
+    statistics and updates running_mean / running_var in place, evaluation mode uses the running statistics (forward only).
+    gamma / beta / a are fp32 parameters; a is nn.PReLU()'s single slope."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, prelu_a, residual, running_mean, running_var, training: bool, eps: float, momentum: float):
+        x = x.contiguous()
+        c = gamma.shape[0] if gamma is not None else x.shape[3]
+        mean = rstd = None
+        if gamma is not None:
+            if training:
+                mean, rstd = ops.bn_stats(x, c, eps, momentum, running_mean, running_var)
+            else:
+                mean, rstd = running_mean.detach().float(), torch.rsqrt(running_var.detach().float() + eps)
+        res = residual.contiguous() if residual is not None else None
+        y = torch.empty_like(x)
+        ops.bn_act_fwd(x, c, mean, rstd, gamma.detach() if gamma is not None else None, beta.detach() if beta is not None else None,
+                       prelu_a.detach() if prelu_a is not None else None, res, y)
+        ctx.save_for_backward(x, mean, rstd, gamma, beta, prelu_a)
+        ctx.c, ctx.training, ctx.has_res = c, training, residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, mean, rstd, gamma, beta, prelu_a = ctx.saved_tensors
+        assert gamma is None or ctx.training, "BatchNorm backward is implemented for training-mode statistics only"
+        g = g.contiguous()
+        dx = torch.empty_like(x)
+        dg = db = da = None
+        gbuf = bbuf = abuf = None
+        acc = None
+        if gamma is not None:
+            gbuf, acc, dg = _grad_target(gamma)
+            bbuf, acc_b, db = _grad_target(beta)
+            assert acc == acc_b
+        if prelu_a is not None:
+            abuf, acc_a, da = _grad_target(prelu_a)
+            if acc is None:
+                acc = acc_a
+            elif acc != acc_a:
+                raise NotImplementedError("BatchNorm and PReLU gradients with different accumulation states")
+        ops.bn_act_bwd(g, x, ctx.c, mean, rstd, gamma.detach() if gamma is not None else None,
+                       beta.detach() if beta is not None else None, prelu_a.detach() if prelu_a is not None else None, dx, gbuf, bbuf,
+                       abuf, bool(acc))
+        return dx, dg, db, da, (g if ctx.has_res else None), None, None, None, None, None
+
+
 class AddFn(Function):
     """Skip connection between two NHWC tensors (edsr.py:47, rdn.py:109) as one kernel."""
 

@@ -92,6 +92,11 @@ PROTOTYPES = {
     "srb_set_wgrad_sm_budget": (c_i32, [c_vp, c_i32]),
     "srb_delay": (c_i32, [c_vp, c_i64, c_vp]),
     "srb_patch_batch": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "srb_bn_stats": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i64, c_i32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "srb_bn_act_fwd": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32,
+                               c_vp, c_i32, c_i32, c_vp]),
+    "srb_bn_act_bwd": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                               c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp]),
     "srb_conv_uses_umma": (c_i32, [C.POINTER(ConvDesc)]),
     "srb_wgrad_uses_umma": (c_i32, [C.POINTER(WgradDesc)]),
     "srb_wgrad_plan": (c_i32, [c_i32, c_i32] + [C.POINTER(c_i32)] * 5),

@@ -492,6 +492,35 @@ def wgrad_overlap_section(used_cluster: bool):
     return contextlib.nullcontext()
 
 
+def bn_stats(x, c, eps, momentum, running_mean=None, running_var=None):
+    """Batch statistics of an NHWC tensor's first c channels: (mean [c], rstd [c]) fp32; the running statistics are updated
+    in place as nn.BatchNorm2d does in training mode."""
+    n, h, w, cs = _nhwc(x)
+    mean = torch.empty(c, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(c, dtype=torch.float32, device=x.device)
+    ws = torch.empty(2 * c, dtype=torch.float32, device=x.device)
+    L.check(L.load().srb_bn_stats(_ctx(x), _p(x), cs, 0, c, n * h * w, dtype_code(x), float(eps), float(momentum), _p(ws), _p(mean),
+                                  _p(rstd), _p(running_mean), _p(running_var), _stream()), "srb_bn_stats")
+    return mean, rstd
+
+
+def bn_act_fwd(x, c, mean, rstd, gamma, beta, prelu_a, res, y):
+    n, h, w, cs = _nhwc(x)
+    L.check(L.load().srb_bn_act_fwd(_ctx(x), _p(x), cs, 0, c, n * h * w, dtype_code(x), _p(mean), _p(rstd), _p(gamma), _p(beta),
+                                    _p(prelu_a), _p(res), res.shape[3] if res is not None else 0, 0, _p(y), y.shape[3], 0, _stream()),
+            "srb_bn_act_fwd")
+    return y
+
+
+def bn_act_bwd(g, x, c, mean, rstd, gamma, beta, prelu_a, dx, dgamma, dbeta, da, accumulate):
+    n, h, w, cs = _nhwc(x)
+    ws = torch.empty(3 * c, dtype=torch.float32, device=x.device)
+    L.check(L.load().srb_bn_act_bwd(_ctx(x), _p(g), g.shape[3], 0, _p(x), cs, 0, c, n * h * w, dtype_code(x), _p(mean), _p(rstd),
+                                    _p(gamma), _p(beta), _p(prelu_a), _p(ws), _p(dx), dx.shape[3], 0, _p(dgamma), _p(dbeta), _p(da),
+                                    1 if accumulate else 0, _stream()), "srb_bn_act_bwd")
+    return dx
+
+
 def bias_grad(gy, g_co, cout, dbias, *, accumulate=False, alpha=1.0, shuffle=0):
     """dbias (+)= alpha * per-channel sums of gy (`shuffle` > 1: gy's channels are in (sub-pixel, c') order, dbias in the
     parameter's), as a deferred item when a queue is active (it then shares the batch's one column-sum launch), else at once."""

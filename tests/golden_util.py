@@ -62,6 +62,8 @@ class Golden:
             cfg.update(n_resblocks=k["n_resblocks"], n_resgroups=k["n_resgroups"])
         elif self.cls == "RDN":
             cfg.update(rdn_config=k["rdn_config"])
+        elif self.cls == "SRResNet":
+            cfg.update(n_resblocks=k["n_resblocks"], n_feats=k["n_feats"])
         elif self.cls == "WDSR":
             cfg.update(type=k["type"], n_feats=k["n_feats"], n_resblocks=k["n_resblocks"], res_scale=k["res_scale"])
         return cfg

@@ -22,7 +22,8 @@ def test_state_dict_layout_matches_golden(name):
     sd = m.state_dict()
     assert list(sd.keys()) == list(g.shapes.keys())
     for k, v in sd.items():
-        assert tuple(v.shape) == g.shapes[k] and v.dtype == torch.float32, k
+        want = torch.int64 if k.endswith("num_batches_tracked") else torch.float32       # (BatchNorm's step counter, SRResNet)
+        assert tuple(v.shape) == g.shapes[k] and v.dtype == want, k
     trainable = [k for k, p in m.named_parameters() if p.requires_grad]
     assert trainable == g.grad_names
     m.load_state_dict({k: torch.from_numpy(v) for k, v in g.state_dict().items()})
@@ -37,6 +38,8 @@ def test_state_dict_layout_matches_golden(name):
     ("SRCNN", dict(scale_factor=3)),
     ("WDSR", dict(type="B", n_feats=128, n_resblocks=16, scale_factor=4)),
     ("WDSR", dict(type="A", n_feats=32, n_resblocks=3, scale_factor=2)),
+    ("SRResNet", dict(n_resblocks=16, n_feats=64, scale_factor=4)),
+    ("SRResNet", dict(n_resblocks=2, n_feats=64, scale_factor=3)),
 ])
 def test_state_dict_layout_matches_reference(cls, kw):
     import models
@@ -58,8 +61,8 @@ def test_state_dict_layout_matches_reference(cls, kw):
 def test_registry_and_signatures():
     import inspect
     import models
-    assert set(models.__all__) == {"EDSR", "RCAN", "RDN", "SRCNN", "SRModel", "WDSR"}
-    for cls in ("EDSR", "RCAN", "RDN", "SRCNN", "WDSR"):
+    assert set(models.__all__) == {"EDSR", "RCAN", "RDN", "SRCNN", "SRModel", "SRResNet", "WDSR"}
+    for cls in ("EDSR", "RCAN", "RDN", "SRCNN", "SRResNet", "WDSR"):
         assert issubclass(getattr(models, cls), models.SRModel)
     assert list(inspect.signature(models.EDSR.__init__).parameters)[1:4] == ["n_feats", "n_resblocks", "res_scale"]
     assert list(inspect.signature(models.RCAN.__init__).parameters)[1:6] == ["n_feats", "n_resblocks", "n_resgroups", "reduction", "res_scale"]
@@ -186,7 +189,7 @@ def test_integration_option_b_registry_snippet_runs(tmp_path):
         "models_b200 = importlib.util.module_from_spec(_spec)\n"
         "sys.modules['models_b200'] = models_b200\n"
         "_spec.loader.exec_module(models_b200)\n"
-        "from models_b200 import EDSR, RCAN, RDN, SRCNN, WDSR, SRModel\n")
+        "from models_b200 import EDSR, RCAN, RDN, SRCNN, SRResNet, WDSR, SRModel\n")
     out = _run("import models; m = models.EDSR(n_resblocks=1); assert issubclass(models.EDSR, models.SRModel); "
                "print('OK', type(m).__module__, len(m.state_dict()))", cwd=str(tmp_path))
     assert "OK models_b200.edsr" in out

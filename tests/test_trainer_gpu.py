@@ -11,6 +11,7 @@ CASES = [
     ("EDSR", dict(n_feats=64, n_resblocks=3, res_scale=0.5, scale_factor=2)),
     ("RDN", dict(rdn_config="B", scale_factor=2)),
     ("WDSR", dict(type="B", n_feats=64, n_resblocks=2, scale_factor=2)),     # weight-norm: g / v gradients come from autograd
+    ("SRResNet", dict(n_resblocks=2, n_feats=64, scale_factor=2)),           # BatchNorm (batch statistics) + PReLU, shared modules
 ]
 
 
@@ -51,12 +52,18 @@ def test_trainstep_matches_autograd_adam_bf16(cls, kwargs, use_graph):
     ts.flat.flat.copy_(snap[0]); ts.flat.m.copy_(snap[1]); ts.flat.v.copy_(snap[2]); ts.flat.step_dev.zero_()
     losses = [ts.step(x.cuda(), hr.cuda()).item() for x, hr in data]
     try:
+        # SRResNet: the loss drops 40 % in two steps at this learning rate and BatchNorm couples every pixel, so the different
+        # summation orders of the two paths (atomics, batched launches) show up a little earlier: 2.6e-3 measured on step 3
+        ltol, ptol = (6e-3, 1.5e-2) if cls == "SRResNet" else (2e-3, 5e-3)
         for a, b in zip(losses, ref_losses):
-            assert abs(a - b) < 2e-3 * abs(b), (losses, ref_losses)
+            assert abs(a - b) < ltol * abs(b), (losses, ref_losses)
+        import re
         for (k, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
             if p.requires_grad:
+                if cls == "SRResNet" and re.fullmatch(r"body\.\d+\.(body\.)?[0134]\.bias", k):
+                    continue      # a conv bias in front of a BatchNorm has zero gradient: Adam turns its rounding noise into +-lr steps
                 d = (p.detach() - q.detach()).norm() / q.detach().norm().clamp_min(1e-12)
-                assert d < 5e-3, (k, d.item())
+                assert d < ptol, (k, d.item())
         assert ts.launches_per_step > 0
     finally:
         ts.close()
@@ -85,11 +92,20 @@ def test_trainstep_fp32_matches_oracle_adam(cls, kwargs):
     sd = {}
     params = []
     for k, v in sd0.items():
+        if k.endswith("num_batches_tracked"):
+            sd[k] = v.clone()
+            continue
         t = v.double().clone()
-        if not k.startswith(("sub_mean", "add_mean")):
+        if not k.startswith(("sub_mean", "add_mean")) and not k.endswith(("running_mean", "running_var")):
             t.requires_grad_(True)
-            params.append(t)
         sd[k] = t
+    if cls == "SRResNet":
+        sd = sr_oracle._srresnet_alias(sd)          # shared BatchNorm / PReLU modules: one tensor under both keys
+    seen = set()
+    for k, t in sd.items():
+        if t.requires_grad and id(t) not in seen:
+            seen.add(id(t))
+            params.append(t)
     opt = torch.optim.Adam(params, lr=1e-3)
     cfg = {"scale": s}
     if cls == "RCAN":
@@ -98,6 +114,8 @@ def test_trainstep_fp32_matches_oracle_adam(cls, kwargs):
         cfg.update(n_resblocks=kwargs["n_resblocks"], res_scale=kwargs["res_scale"])
     elif cls == "WDSR":
         cfg.update(type=kwargs["type"], n_feats=kwargs["n_feats"], n_resblocks=kwargs["n_resblocks"])
+    elif cls == "SRResNet":
+        cfg.update(n_feats=kwargs["n_feats"], n_resblocks=kwargs["n_resblocks"])
     else:
         cfg.update(rdn_config=kwargs["rdn_config"])
     ref_losses = []
@@ -111,8 +129,11 @@ def test_trainstep_fp32_matches_oracle_adam(cls, kwargs):
         for a, b in zip(losses, ref_losses):
             assert abs(a - b) < 1e-5 * abs(b), (losses, ref_losses)
         worst = 0.0
+        import re
         for k, p in m.named_parameters():
             if p.requires_grad:
+                if cls == "SRResNet" and re.fullmatch(r"body\.\d+\.(body\.)?[0134]\.bias", k):
+                    continue      # zero-gradient parameters (conv bias in front of BatchNorm): Adam amplifies rounding noise
                 d = ((p.detach().double().cpu() - sd[k].detach()).norm() / sd[k].detach().norm().clamp_min(1e-12)).item()
                 worst = max(worst, d)
         # Adam's m/sqrt(v) turns a 1e-7 gradient difference into an O(lr) update difference only for
