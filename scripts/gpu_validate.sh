@@ -1,15 +1,14 @@
+# full validation on one B200: GPU tests, the default bench line (both timed), optionally the ncu launch list and full captures
 mkdir -p gpurun_out
 ( time timeout 1500 python -m pytest tests -m gpu -x -q ) > gpurun_out/final_tests.log 2>&1
-tail -4 gpurun_out/final_tests.log
+grep -E "passed|failed|error" gpurun_out/final_tests.log | tail -3
 ( time timeout 900 python bench.py ) > gpurun_out/final_bench_default.log 2>&1
-tail -c 400 gpurun_out/final_bench_default.log
-# launch list of one captured training step (device time per kernel; shares only)
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 0 -c 1500 --csv --log-file gpurun_out/r02_launches_rcan.csv python bench.py --workload train --steps 1 --warmup 1 --no-extras --no-cpu-baseline --sustain-seconds 0 > gpurun_out/final_ncu_launches.log 2>&1
-tail -2 gpurun_out/final_ncu_launches.log | cut -c1-200
-# full captures
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:chain_cluster -s 2 -c 1 -f -o gpurun_out/r02_chain_cluster_bwd python scripts/ncu_targets.py group 2>&1 | tail -2
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_chain_kernel -s 2 -c 1 -f -o gpurun_out/r02_chain_flags_fwd python scripts/ncu_targets.py group 2>&1 | tail -2
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_wide -s 2 -c 1 -f -o gpurun_out/r02_conv_wide128 python scripts/ncu_targets.py wide128 2>&1 | tail -2
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:wgrad_umma -s 2 -c 2 -f -o gpurun_out/r02_wgrad_group python scripts/ncu_targets.py wgrad 2>&1 | tail -2
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:wgrad_umma -s 4 -c 2 -f -o gpurun_out/r02_wgrad_group_52sm python scripts/ncu_targets.py wgrad 52 2>&1 | tail -2
-ls -la gpurun_out/*.ncu-rep
+tail -c 300 gpurun_out/final_bench_default.log
+if [ "$1" = "ncu" ]; then
+  # launch list of the timed step only (device time per kernel; serialised: use for shares)
+  SRB200_NCU_RANGE=1 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_rcan.csv python bench.py --workload train --steps 1 --warmup 1 --no-extras --no-cpu-baseline --sustain-seconds 0 > gpurun_out/final_ncu_launches.log 2>&1
+  for t in "chain_cluster group r02_chain_cluster_bwd" "conv_chain_kernel group r02_chain_flags_fwd" "conv_wide wide128 r02_conv_wide128" "wgrad_umma wgrad r02_wgrad_group"; do
+    set -- $t
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:$1 -s 2 -c 1 -f -o gpurun_out/$3 python scripts/ncu_targets.py $2 2>&1 | tail -1
+  done
+fi

@@ -629,10 +629,11 @@ def pixel_unshuffle(g, r, cp=None):
     """cp: logical channels of g (default: all of them); g may be wider (bf16 tensors keep pixels 16-byte aligned, so the
     3-channel output of WDSR's shuffled tail / skip convs is stored 8 wide)."""
     n, hr, wr, gcs = _nhwc(g)
+    padded_out = cp is not None
     cp = gcs if cp is None else cp
     h, w = hr // r, wr // r
     ocs = cp * r * r
-    if g.dtype == torch.bfloat16 and ocs % 8:
+    if padded_out and g.dtype == torch.bfloat16 and ocs % 8:     # the consumer is a conv kernel: its tensors keep 16-byte pixels
         ocs = (ocs + 7) // 8 * 8
     out = torch.empty((n, h, w, ocs), dtype=g.dtype, device=g.device)
     L.check(L.load().srb_pixel_unshuffle(_ctx(g), _p(g), gcs, 0, _p(out), ocs, 0, n, h, w, cp, r, dtype_code(g),
