@@ -204,10 +204,6 @@ typedef struct srb_chain_op {
   float   *ca_s, *ca_y;                         /* [N][64]: written by SRB_CHAIN_CA, read by CA_BWD */
   float   *ca_dw1, *ca_db1, *ca_dw2, *ca_db2;   /* CA_BWD: accumulated */
   float   *ca_scratch;                          /* CA_BWD: [N][64] zero-filled */
-  const float* ca_poolmat;  /* SRB_CHAIN_CA, optional: the conv's tap-summed filters from srb_chain_poolmats, [9][64 ci][64 co]
-                               fp32.  When given and the previous op is a plain conv that produces this op's input, that op's tiles
-                               publish the pooled sums of THIS op (the mean of a conv is linear in its input) and the CALayer op runs
-                               as a single pass instead of waiting, mid-op, for every tile of its sample. */
 } srb_chain_op;
 
 typedef struct srb_chain_desc {
@@ -227,11 +223,6 @@ typedef struct srb_chain_desc {
                                          L2-flag kernel (all SMs, faster for forward chains that run alone); 2 = 0 */
 } srb_chain_desc;
 int  srb_conv_chain(srb_ctx*, const srb_chain_desc*, void* stream);
-/* Tap-summed filters of layers `layers[0..n)` of a packed 3x3 64->64 filter bank (SRB_PACK_UMMA, forward), for
- * srb_chain_op.ca_poolmat: out[i][m][ci][co] fp32 with m = 0: sum over all nine taps; 1: taps with kh = 2; 2: kh = 0; 3: kw = 2;
- * 4: kw = 0; 5..8: the single taps (kh,kw) = (2,2), (2,0), (0,2), (0,0).  (Summing a conv's output over the image = applying
- * these to the column sums of its input, minus the image row / column that zero padding replaces for a tap.) */
-int  srb_chain_poolmats(srb_ctx*, const void* bank, const int32_t* layers_host, int n, float* out, void* stream);
 /* 1 if srb_conv_chain runs this chain with the per-sample thread-block-cluster kernel (conv_cluster.cu: H % 16 == 0,
  * W in {24, 48}, at most 8 CTAs of 16 x 24 pixels per sample, every op a conv that consumes the previous op's result;
  * activations stay in shared memory between layers, halos travel through distributed shared memory), 0 if it takes the

@@ -214,13 +214,9 @@ def stage_rcab(shape, blocks=2):
     ch.space(1, x.view(1, n, h, w, 64))
     ref = ops.Chain.ref
     c = ref(1, 0)
-    # tap-summed filters: the L2-flag kernel then publishes a CALayer op's pool from the PREVIOUS op's tiles (ignored by the
-    # cluster kernel); block 0's conv1 is op 0, so every CALayer op here has a plain conv in front of it
-    G = ops.chain_poolmats(bank, [2 * b + 1 for b in range(blocks)]) if ops.chain_ca_prepool() else None
     for b in range(blocks):
         ch.conv(c, ref(0, 3 * b), 2 * b, bs[2 * b], relu=True)
-        ch.conv_ca(ref(0, 3 * b), ref(0, 3 * b + 1), ref(0, 3 * b + 2), c, 2 * b + 1, bs[2 * b + 1], pools[b], *cas[b], ss[b], ys[b],
-                   poolmat=G[b] if G is not None else None)
+        ch.conv_ca(ref(0, 3 * b), ref(0, 3 * b + 1), ref(0, 3 * b + 2), c, 2 * b + 1, bs[2 * b + 1], pools[b], *cas[b], ss[b], ys[b])
         c = ref(0, 3 * b + 2)
     ch.conv(c, ref(0, 3 * blocks), 2 * blocks, bs[-1], relu=True)
     ch.run(bank)
@@ -347,8 +343,6 @@ STAGES = {
     "rcab1": lambda: stage_rcab((2, 16, 24)),
     "rcab2": lambda: stage_rcab((2, 32, 48)),
     "rcab6": lambda: stage_rcab((16, 48, 48), 3),
-    "rcabr": lambda: stage_rcab((3, 40, 44), 2),          # ragged: L2-flag kernel, image borders inside tiles
-    "rcabs": lambda: stage_rcab((2, 16, 8), 2),           # one tile per sample: every border in the same tile
     "rcan": lambda: stage_model("rcan"),
     "edsr": lambda: stage_model("edsr"),
 }

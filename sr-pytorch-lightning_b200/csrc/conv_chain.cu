@@ -44,8 +44,6 @@ constexpr uint32_t kTmemCols = 128;
 constexpr int kMaxCr = 16;
 constexpr uint32_t kScaled = 1u << 16;    // epilogue specialisation keys: scale != 1 / no specialisation
 constexpr uint32_t kGeneric = 1u << 17;
-constexpr uint32_t kPooled = 1u << 18;    // CALayer op whose pooled sums the PREVIOUS op has already published: single-pass epilogue
-enum { SIDE_PRE_POOL = 1, SIDE_POOLED = 2 };
 
 struct ChainMaps {
   CUtensorMap win[4];    // 5-D (c, w, h, n, slot), box 64 x 10 x 18
@@ -61,7 +59,6 @@ struct ChainParams {
   int* tile_flags;       // NULL, or [n_ops][total_tiles]: per-tile completion flags instead of per-sample counts
   long long* trace;
   srb_chain_op ops[SRB_CHAIN_MAX_OPS];
-  uint8_t side[SRB_CHAIN_MAX_OPS];   // SIDE_*: see "pool of a conv from its input's column sums" in the epilogue
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -209,9 +206,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float bias_s[2][64];
   __shared__ float colsum_s[2][4][64];
-  __shared__ __align__(16) float ca_s[2][64], ca_y[2][64], ca_du[2][64], ca_ds[2][64], ca_z[2][kMaxCr], ca_dv[2][kMaxCr];
-  __shared__ __align__(16) float bvec[2][9][64];   // per chain: column sums of a staged tile — all pixels, top / bottom image row, left / right
-                                                   // image column — and the four image-corner pixels (rows 5-8, order of ca_poolmat)
+  __shared__ float ca_s[2][64], ca_y[2][64], ca_du[2][64], ca_ds[2][64], ca_z[2][kMaxCr], ca_dv[2][kMaxCr];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -448,19 +443,11 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
     const uint32_t e2row = e2buf + (uint32_t)row * 128u;
     const float inv_hw = 1.f / (float)(p.H * p.W);
     uint32_t a_k = 0, e_k = 0, e2_k = 0, acc_k = 0;
-    auto stg_value = [&](const int px, const int ch) {      // one bf16 channel of pixel px of the staged tile
-      uint16_t r16;
-      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r16)
-                   : "r"(stg + (uint32_t)px * 128u + ((((uint32_t)ch >> 3) ^ ((uint32_t)px & 7u)) << 4) + ((uint32_t)ch & 7u) * 2u)
-                   : "memory");
-      return __uint_as_float((uint32_t)r16 << 16);
-    };
 
     for (int op = 0; op < p.n_ops; ++op) {
       const srb_chain_op& o = p.ops[op];
       const uint32_t flags = o.flags;
       const int Cr = o.ca_cr;
-      const uint32_t side = p.side[op];
       for (int j = c; j < my_tiles; j += 2) {
         const int t = bid + j * grid;
         const int n = t / p.tiles_per_sample;
@@ -606,55 +593,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
           const bool ca = (flags & SRB_CHAIN_CA) != 0;
           // the bias of this op is cold in L1 (every op has its own): fetch it into shared memory
           // while the MMAs run instead of stalling each 32-column chunk on an L2 round trip
-          const bool pooled = ca && (side & SIDE_POOLED);
-          const float bias_own = (row < 64 && o.bias) ? __ldg(o.bias + row) : 0.f;
-          if (row < 64) bias_s[c][row] = bias_own;
-          if (pooled) {
-            // The sample's pooled sums were published by the tiles of the PREVIOUS op (SIDE_PRE_POOL below) about one op period
-            // ago: evaluate the gate now, while this tile's MMAs run, and apply it in the one pass over the accumulator.
-            float w1a[2] = {0.f, 0.f}, w1b[2] = {0.f, 0.f}, b1v[2] = {0.f, 0.f};
-            {
-              int u = 0;
-              for (int jj = q; jj < Cr && u < 2; jj += 4, ++u) {
-                w1a[u] = __ldg(o.ca_w1 + jj * 64 + lane);
-                w1b[u] = __ldg(o.ca_w1 + jj * 64 + lane + 32);
-                b1v[u] = __ldg(o.ca_b1 + jj);
-              }
-            }
-            float w2r[4] = {0.f, 0.f, 0.f, 0.f}, b2v = 0.f;
-            if (row < 64) {
-              b2v = __ldg(o.ca_b2 + row);
-              for (int jj = 0; jj < Cr && jj < 4; ++jj) w2r[jj] = __ldg(o.ca_w2 + row * Cr + jj);
-            }
-            if (store_thread) {
-              wait_counter(cnt_part, p.tiles_per_sample);
-              CH_TRACE(c, op, TR_POOL);
-            }
-            ptx::named_bar_sync(bar_id, 128);
-            // colsum holds the sample's sum of conv(x) WITHOUT the bias; mean(t) = that / HW + bias
-            if (row < 64) ca_s[c][row] = fmaf(__ldcg(o.colsum + (int64_t)n * 64 + row), inv_hw, bias_own);
-            ptx::named_bar_sync(bar_id, 128);
-            {
-              int u = 0;
-              for (int jj = q; jj < Cr; jj += 4, ++u) {
-                float a = (u < 2 ? w1a[u] : __ldg(o.ca_w1 + jj * 64 + lane)) * ca_s[c][lane] +
-                          (u < 2 ? w1b[u] : __ldg(o.ca_w1 + jj * 64 + lane + 32)) * ca_s[c][lane + 32];
-                a = warp_sum(a);
-                if (lane == 0) ca_z[c][jj] = fmaxf(a + (u < 2 ? b1v[u] : __ldg(o.ca_b1 + jj)), 0.f);
-              }
-            }
-            ptx::named_bar_sync(bar_id, 128);
-            if (row < 64) {
-              float u = b2v;
-              for (int jj = 0; jj < Cr; ++jj) u += (jj < 4 ? w2r[jj] : __ldg(o.ca_w2 + row * Cr + jj)) * ca_z[c][jj];
-              const float yv = 1.f / (1.f + expf(-u));
-              ca_y[c][row] = yv;
-              if (r == 0) {
-                o.ca_s[(int64_t)n * 64 + row] = ca_s[c][row];
-                o.ca_y[(int64_t)n * 64 + row] = yv;
-              }
-            }
-          }
+          if (row < 64) bias_s[c][row] = o.bias ? __ldg(o.bias + row) : 0.f;
           ptx::named_bar_sync(bar_id, 128);
           ptx::mbar_wait(&acc_full[c], acc_k & 1u);
           ptx::tc_fence_after();
@@ -669,7 +608,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
             ptx::tmem_ld_32x32b_x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 64), acc2[0]);
             ptx::tmem_ld_32x32b_x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 64 + 32), acc2[1]);
             ptx::tmem_ld_wait();
-            const uint32_t fl = (F == kGeneric) ? flags : (F & 0xFFFFu);
+            const uint32_t fl = (F == kGeneric) ? flags : F;
             const float scale = o.scale;
 #pragma unroll
             for (int hc = 0; hc < 2; ++hc) {
@@ -723,30 +662,9 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
               for (int g = 0; g < 4; ++g)
                 ptx::sts128(orow + ((((uint32_t)(c0 >> 3) + g) ^ sw) << 4),
                             make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]));
-              if (F & kPooled) {      // out = t * gate + skip, written over the skip tile (t as stored: bf16)
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                  const uint32_t off = (((uint32_t)(c0 >> 3) + g) ^ sw) << 4;
-                  const uint4 xv = ptx::lds128(erow + off);
-                  const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-                  const float4 ya = *reinterpret_cast<const float4*>(&ca_y[c][c0 + g * 8]);
-                  const float4 yb = *reinterpret_cast<const float4*>(&ca_y[c][c0 + g * 8 + 4]);
-                  const float y8[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
-                  uint32_t pk[4];
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 ft = unpack_bf16x2(packed[g * 4 + e]), fx = unpack_bf16x2(xw[e]);
-                    pk[e] = valid ? pack_bf16x2(fmaf(ft.x, y8[e * 2], fx.x), fmaf(ft.y, y8[e * 2 + 1], fx.y)) : 0u;
-                  }
-                  ptx::sts128(erow + off, make_uint4(pk[0], pk[1], pk[2], pk[3]));
-                }
-              }
             }
           };
-          switch ((flags & 47u) | (o.scale != 1.f ? kScaled : 0u) | (pooled ? kPooled : 0u)) {
-            case SRB_RESIDUAL | SRB_COLSUM | SRB_CHAIN_CA | kPooled:
-              epilogue(std::integral_constant<uint32_t, SRB_RESIDUAL | SRB_COLSUM | SRB_CHAIN_CA | kPooled>{});
-              break;
+          switch ((flags & 47u) | (o.scale != 1.f ? kScaled : 0u)) {
             case SRB_RELU: epilogue(std::integral_constant<uint32_t, SRB_RELU>{}); break;
             case SRB_RESIDUAL: epilogue(std::integral_constant<uint32_t, SRB_RESIDUAL>{}); break;
             case SRB_RESIDUAL | kScaled: epilogue(std::integral_constant<uint32_t, SRB_RESIDUAL | kScaled>{}); break;
@@ -761,7 +679,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
           ptx::tc_fence_before();
           ptx::fence_proxy_async_smem();
           ptx::named_bar_sync(bar_id, 128);
-          if (ca && !pooled) {
+          if (ca) {
             // CALayer pool (needed before anything else can happen): sums of the STORED (bf16-rounded) values,
             // read back from the staged tile (the register butterfly this replaces cost ~1 us per tile); the
             // four warps' partial sums meet in shared memory so that a tile issues 64 atomics, not 256
@@ -797,14 +715,6 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
               }
               if (o.colsum2) late_colsum(e2buf, o.colsum2, 0.f);
               ++e2_k;
-            }
-          } else if (pooled) {
-            if (store_thread) {
-              ptx::mbar_arrive(&acc_empty[c]);
-              tma_store_5d(&maps.tile[ref_space(o.y)], stg, 0, w0, h0, n, ref_slot(o.y));
-              tma_store_5d(&maps.tile[ref_space(o.y2)], ebuf, 0, w0, h0, n, ref_slot(o.y2));
-              ptx::bulk_commit_group();
-              CH_TRACE(c, op, TR_STAGED);
             }
           } else {
             // ---- CALayer gate + RCAB skip (rcan.py:10-29,54) on the tile still in the staging buffer ----
@@ -921,105 +831,6 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
           else red_release_gpu(cnt_done, 1);
           CH_TRACE(c, op, TR_RELEASED);
         }
-        if (side & SIDE_PRE_POOL) {
-          // ---- this tile's share of the NEXT op's CALayer pool, from the tile just staged (r = relu(conv1)) ----
-          // mean_p(conv2(r) + b)[co] = b[co] + 1/HW sum_{tap,ci} W2[tap][co][ci] * S_tap[ci], where S_tap[ci] sums r[., ci] over
-          // the pixels tap reads for SOME output pixel: the whole image minus the row / column that zero padding replaces
-          // (kh = 2 never reads the top image row, kh = 0 never the bottom row, kw = 2 / kw = 0 the left / right column; the
-          // corner pixel of two such exclusions comes back once).  The sum is linear, so every tile applies conv2's
-          // tap-SUMMED filters G (srb_chain_poolmats, L2-resident) to the column sums of its own pixels and adds 64 numbers to
-          // the sample's pool — after this tile has been released to its consumers (off the dependency chain), one op period
-          // before conv2's epilogue needs the gate.
-          const srb_chain_op& o2 = p.ops[op + 1];
-          const float* G = o2.ca_poolmat;
-          const int rb = p.H - 1 - h0, cb = p.W - 1 - w0;
-          const bool has_top = h0 == 0, has_bot = rb < kTH, has_left = w0 == 0, has_right = cb < kTW;
-          tile_colsum_lds(stg, q, lane, colsum_s[c][q]);
-          {
-            const int vec = row >> 6, ch = row & 63;      // vec 0: top row, left column; vec 1: bottom row, right column
-            const bool hr = vec == 0 ? has_top : has_bot, hc = vec == 0 ? has_left : has_right;
-            const int rr = vec == 0 ? 0 : rb, cc = vec == 0 ? 0 : cb;
-            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-            if (hr) {
-#pragma unroll
-              for (int x = 0; x < kTW; x += 2) {
-                a0 += stg_value(rr * kTW + x, ch);
-                a1 += stg_value(rr * kTW + x + 1, ch);
-              }
-            }
-            if (hc) {
-#pragma unroll
-              for (int y = 0; y < kTH; y += 2) {
-                b0 += stg_value(y * kTW + cc, ch);
-                b1 += stg_value((y + 1) * kTW + cc, ch);
-              }
-            }
-            bvec[c][1 + vec][ch] = a0 + a1;
-            bvec[c][3 + vec][ch] = b0 + b1;
-          }
-          ptx::named_bar_sync(bar_id, 128);
-          if (row < 64) {
-            bvec[c][0][row] = (colsum_s[c][0][row] + colsum_s[c][1][row]) + (colsum_s[c][2][row] + colsum_s[c][3][row]);
-            if (has_top && has_left) bvec[c][5][row] = stg_value(0, row);
-            if (has_top && has_right) bvec[c][6][row] = stg_value(cb, row);
-            if (has_bot && has_left) bvec[c][7][row] = stg_value(rb * kTW, row);
-            if (has_bot && has_right) bvec[c][8][row] = stg_value(rb * kTW + cb, row);
-          }
-          ptx::named_bar_sync(bar_id, 128);
-          {
-            // terms (matrix m of G, vector m of bvec, sign): the whole tile, minus the excluded row / column sums, plus the
-            // corners taken out twice.  G lives in L2 (no room for it in L1 beside 220 KB of shared memory): the 32 loads of
-            // a term are issued back to back, two terms at a time, so that a tile pays two or three L2 latencies, not 100.
-            const int co = row & 63, half = row >> 6;     // output channel, half of the input channels; G is [m][ci][co]
-            const float* g0 = G + (size_t)(half * 32) * 64 + co;
-            int term[9], nt = 0;
-            term[nt++] = 0;
-            if (has_top) term[nt++] = 1;
-            if (has_bot) term[nt++] = 2;
-            if (has_left) term[nt++] = 3;
-            if (has_right) term[nt++] = 4;
-            if (has_top && has_left) term[nt++] = 5;
-            if (has_top && has_right) term[nt++] = 6;
-            if (has_bot && has_left) term[nt++] = 7;
-            if (has_bot && has_right) term[nt++] = 8;
-            float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 1
-            for (int e = 0; e < nt; e += 2) {
-              const int ma = term[e], mb = e + 1 < nt ? term[e + 1] : -1;
-              float ga[32], gb[32];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) ga[i] = __ldg(g0 + (size_t)ma * 4096 + (size_t)i * 64);
-              if (mb >= 0) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) gb[i] = __ldg(g0 + (size_t)mb * 4096 + (size_t)i * 64);
-              }
-              const float sa = (ma >= 1 && ma <= 4) ? -1.f : 1.f, sb = (mb >= 1 && mb <= 4) ? -1.f : 1.f;
-              const float* xa = &bvec[c][ma][half * 32];
-              float ta = 0.f;
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 xv = *reinterpret_cast<const float4*>(xa + i);
-                ta = fmaf(ga[i], xv.x, ta); ta = fmaf(ga[i + 1], xv.y, ta); ta = fmaf(ga[i + 2], xv.z, ta); ta = fmaf(ga[i + 3], xv.w, ta);
-              }
-              acc0 = fmaf(sa, ta, acc0);
-              if (mb >= 0) {
-                const float* xb = &bvec[c][mb][half * 32];
-                float tb = 0.f;
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  const float4 xv = *reinterpret_cast<const float4*>(xb + i);
-                  tb = fmaf(gb[i], xv.x, tb); tb = fmaf(gb[i + 1], xv.y, tb); tb = fmaf(gb[i + 2], xv.z, tb); tb = fmaf(gb[i + 3], xv.w, tb);
-                }
-                acc1 = fmaf(sb, tb, acc1);
-              }
-            }
-            colsum_s[c][half][co] = acc0 + acc1;      // (the column-sum partials are dead: bvec[c][0] holds their total)
-          }
-          ptx::named_bar_sync(bar_id, 128);
-          if (row < 64) atomicAdd(o2.colsum + (int64_t)n * 64 + row, colsum_s[c][0][row] + colsum_s[c][1][row]);
-          ptx::named_bar_sync(bar_id, 128);      // the 64 contributions precede the cumulative release below
-          if (store_thread) red_release_gpu(p.counters + ((size_t)(op + 1) * 2 + 1) * N + n, 1);
-        }
         ptx::named_bar_sync(bar_id, 128);          // staging buffer free before the next item writes it
       }
     }
@@ -1130,22 +941,6 @@ extern "C" int srb_conv_chain(srb_ctx* ctx, const srb_chain_desc* d, void* strea
     used[sp] = true;
     return 0;
   };
-  // CALayer pool one op early (see SIDE_PRE_POOL in the kernel): a plain conv whose result feeds a CALayer op that brings its
-  // tap-summed filters (ca_poolmat) publishes that op's pooled sums from its own output tiles.  SRB200_CHAIN_CA_PREPOOL=0 keeps
-  // the form in which the CALayer op pools its own result and every tile then waits for the slowest tile of its sample.
-  {
-    const char* e = getenv("SRB200_CHAIN_CA_PREPOOL");
-    const bool on = !(e && e[0] == '0');
-    for (int i = 0; i < SRB_CHAIN_MAX_OPS; ++i) p.side[i] = 0;
-    for (int i = 0; on && i + 1 < d->n_ops; ++i) {
-      const srb_chain_op &o0 = d->ops[i], &o1 = d->ops[i + 1];
-      if (o0.kind == SRB_CHAIN_CONV && o1.kind == SRB_CHAIN_CONV && (o1.flags & SRB_CHAIN_CA) && o1.ca_poolmat != nullptr &&
-          !(o0.flags & (SRB_CHAIN_CA | SRB_CHAIN_CA_BWD_FUSED)) && o1.x == o0.y && o1.colsum != nullptr) {
-        p.side[i] |= SIDE_PRE_POOL;
-        p.side[i + 1] |= SIDE_POOLED;
-      }
-    }
-  }
   bool any_conv = false;
   for (int i = 0; i < d->n_ops; ++i) {
     const srb_chain_op& o = d->ops[i];

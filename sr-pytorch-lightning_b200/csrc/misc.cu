@@ -706,44 +706,3 @@ extern "C" int srb_delay(srb_ctx* ctx, int64_t ns, void* stream) {
   SRB_LAUNCH_CHECK();
   return 0;
 }
-
-// ---- tap-summed filters for the CALayer pool (srb_chain_op.ca_poolmat) -------------------------------------------------
-// bank layer = [kw][kh][cout][cin] bf16 (SRB_PACK_UMMA forward).  out[i][m][ci][co] fp32, m as in include/srb200.h.  The sums
-// are taken over the bf16 values the MMAs use, in fp32.
-struct PoolmatLayers {
-  int32_t layer[SRB_CHAIN_MAX_OPS];
-};
-
-__global__ void __launch_bounds__(256) chain_poolmats_kernel(const __nv_bfloat16* __restrict__ bank, const PoolmatLayers L,
-                                                             float* __restrict__ out) {
-  const __nv_bfloat16* w = bank + (size_t)L.layer[blockIdx.x] * 9 * 64 * 64;
-  float* o = out + (size_t)blockIdx.x * 9 * 64 * 64;
-  for (int idx = threadIdx.x; idx < 64 * 64; idx += 256) {
-    const int co = idx & 63, ci = idx >> 6;
-    float t[3][3];      // [kh][kw]
-#pragma unroll
-    for (int kw = 0; kw < 3; ++kw)
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh) t[kh][kw] = __bfloat162float(w[((size_t)(kw * 3 + kh) * 64 + co) * 64 + ci]);
-    const float row0 = t[0][0] + t[0][1] + t[0][2], row1 = t[1][0] + t[1][1] + t[1][2], row2 = t[2][0] + t[2][1] + t[2][2];
-    const size_t e = (size_t)ci * 64 + co;
-    o[0 * 4096 + e] = row0 + row1 + row2;
-    o[1 * 4096 + e] = row2;                                  // kh = 2
-    o[2 * 4096 + e] = row0;                                  // kh = 0
-    o[3 * 4096 + e] = t[0][2] + t[1][2] + t[2][2];           // kw = 2
-    o[4 * 4096 + e] = t[0][0] + t[1][0] + t[2][0];           // kw = 0
-    o[5 * 4096 + e] = t[2][2];
-    o[6 * 4096 + e] = t[2][0];
-    o[7 * 4096 + e] = t[0][2];
-    o[8 * 4096 + e] = t[0][0];
-  }
-}
-
-extern "C" int srb_chain_poolmats(srb_ctx* ctx, const void* bank, const int32_t* layers_host, int n, float* out, void* stream) {
-  SRB_REQUIRE(ctx && bank && layers_host && out && n > 0 && n <= SRB_CHAIN_MAX_OPS, "srb_chain_poolmats: bad argument");
-  PoolmatLayers L;
-  for (int i = 0; i < n; ++i) L.layer[i] = layers_host[i];
-  chain_poolmats_kernel<<<n, 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(bank), L, out);
-  SRB_LAUNCH_CHECK();
-  return 0;
-}

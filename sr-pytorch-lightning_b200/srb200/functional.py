@@ -261,18 +261,14 @@ class RCANGroupFn(Function):
         ref = ops.Chain.ref
         xin = ref(2, 0)
         cur = xin
-        hint = ops.chain_forward_hint()
-        # L2-flag kernel: conv1's tiles publish conv2's pooled sums (tap-summed filters applied to their column sums)
-        G = ops.chain_poolmats(bank, [2 * b + 1 for b in range(nb)]) if (hint == 1 and ops.chain_ca_prepool()) else None
         for b in range(nb):
             w1, b1, w2, b2, cw1, cb1, cw2, cb2 = (t.detach() for t in params[8 * b:8 * b + 8])
             ch.conv(cur, ref(0, 3 * b), 2 * b, b1, relu=True)
             ch.conv_ca(ref(0, 3 * b), ref(0, 3 * b + 1), ref(0, 3 * b + 2), cur, 2 * b + 1, b2, pool[b],
-                       cw1.reshape(cw1.shape[0], 64), cb1, cw2.reshape(64, cw2.shape[1]), cb2, s_all[b], y_all[b],
-                       poolmat=G[b] if G is not None else None)
+                       cw1.reshape(cw1.shape[0], 64), cb1, cw2.reshape(64, cw2.shape[1]), cb2, s_all[b], y_all[b])
             cur = ref(0, 3 * b + 2)
         ch.conv(cur, ref(0, 3 * nb), 2 * nb, params[-1].detach(), res=xin)
-        ch.run(bank, hint=hint)
+        ch.run(bank, hint=ops.chain_forward_hint())
         ctx.save_for_backward(x, A, s_all, y_all, *params)
         ctx.owner, ctx.nb = owner, nb
         return A[3 * nb]

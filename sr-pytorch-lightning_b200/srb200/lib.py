@@ -57,7 +57,7 @@ class ChainOp(C.Structure):
                 ("colsum_groups", c_i32), ("ca_cr", c_i32), ("colsum_scale", c_f32),
                 ("bias", c_vp), ("colsum", c_vp), ("colsum2", c_vp), ("ca_w1", c_vp), ("ca_b1", c_vp), ("ca_w2", c_vp), ("ca_b2", c_vp),
                 ("ca_s", c_vp), ("ca_y", c_vp), ("ca_dw1", c_vp), ("ca_db1", c_vp), ("ca_dw2", c_vp), ("ca_db2", c_vp),
-                ("ca_scratch", c_vp), ("ca_poolmat", c_vp)]
+                ("ca_scratch", c_vp)]
 
 
 class ChainDesc(C.Structure):
@@ -91,7 +91,6 @@ PROTOTYPES = {
     "srb_conv_wgrad_batched": (c_i32, [c_vp, C.POINTER(WgradItem), c_i32, c_vp]),
     "srb_set_wgrad_sm_budget": (c_i32, [c_vp, c_i32]),
     "srb_delay": (c_i32, [c_vp, c_i64, c_vp]),
-    "srb_chain_poolmats": (c_i32, [c_vp, c_vp, C.POINTER(c_i32), c_i32, c_vp, c_vp]),
     "srb_patch_batch": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "srb_bn_stats": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i64, c_i32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "srb_bn_act_fwd": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32,

@@ -695,23 +695,6 @@ class FilterBank:
         return bank
 
 
-def chain_poolmats(bank: torch.Tensor, layers, out: torch.Tensor | None = None) -> torch.Tensor:
-    """Tap-summed filters [len(layers), 9, 64, 64] fp32 of layers of a forward filter bank (srb_chain_poolmats)."""
-    n = len(layers)
-    if out is None:
-        out = torch.empty((n, 9, 64, 64), dtype=torch.float32, device=bank.device)
-    arr = (C.c_int32 * n)(*[int(v) for v in layers])
-    L.check(L.load().srb_chain_poolmats(_ctx(bank), _p(bank), arr, n, _p(out), _stream()), "srb_chain_poolmats")
-    return out
-
-
-def chain_ca_prepool() -> bool:
-    """CALayer pool published one op early by the L2-flag chain kernel (srb_chain_op.ca_poolmat); SRB200_CHAIN_CA_PREPOOL=0
-    keeps the two-pass CALayer op."""
-    import os
-    return os.environ.get("SRB200_CHAIN_CA_PREPOOL", "1") not in ("", "0")
-
-
 def chain_forward_hint() -> int:
     """Kernel for FORWARD chains (srb_chain_desc.kernel_hint).  Nothing else runs beside a forward chain, so the L2-flag
     kernel, which spreads the tiles over all SMs, is the faster one there (RCAN ResidualGroup on [16,48,48,64]: 271 us
@@ -803,12 +786,9 @@ class Chain:
         o.colsum_scale = float(colsum_scale)
         return o
 
-    def conv_ca(self, x, t, out, skip, w_layer, bias, pool, w1, b1, w2, b2, s_out, y_out, poolmat=None):
-        """RCAB second conv + CALayer + skip: t = conv(x)+bias -> slot t; out = t*gate + skip.
-        poolmat: this layer's tap-summed filters [9,64,64] fp32 (chain_poolmats): the L2-flag kernel then lets the PREVIOUS
-        op's tiles publish the pooled sums and runs this op as a single pass (`pool` then holds the sums without the bias)."""
+    def conv_ca(self, x, t, out, skip, w_layer, bias, pool, w1, b1, w2, b2, s_out, y_out):
+        """RCAB second conv + CALayer + skip: t = conv(x)+bias -> slot t; out = t*gate + skip."""
         o = self.conv(x, t, w_layer, bias, res=skip, colsum=pool, colsum_groups=self.n)
-        o.ca_poolmat = self._ptr(poolmat)
         o.flags |= L.CHAIN_CA
         o.y2 = out
         o.ca_cr = w1.shape[0]

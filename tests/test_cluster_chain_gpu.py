@@ -46,20 +46,6 @@ def test_cluster_rcab_chain_forward(shape, blocks):
     assert _dbg().stage_rcab(shape, blocks)
 
 
-@pytest.mark.parametrize("shape", [(2, 16, 8), (2, 16, 24), (3, 40, 44), (3, 32, 48), (16, 48, 48), (1, 56, 72)])
-@pytest.mark.parametrize("prepool", ["1", "0"])
-def test_flag_chain_rcab_forward_pool_one_op_early(shape, prepool):
-    """L2-flag chain kernel (SRB200_CHAIN_CLUSTER=0): with the tap-summed filters given, conv1's tiles publish conv2's pooled
-    sums (the mean of a conv is linear in its input; the image border drops a row / column per tap) and the CALayer op is a
-    single pass — against the per-layer kernels, on shapes with one tile per sample, ragged tiles and every border
-    combination; prepool = 0 is the two-pass form."""
-    env = dict(os.environ, SRB200_CHAIN_CLUSTER="0", SRB200_CHAIN_CA_PREPOOL=prepool)
-    code = f"import sys; sys.path.insert(0, {os.path.join(ROOT, 'scripts')!r}); import cluster_debug as d; sys.exit(0 if d.stage_rcab({shape!r}, 3) else 1)"
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
-    print(r.stdout[-1500:])
-    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
-
-
 @pytest.mark.parametrize("shape", [(2, 16, 24), (3, 32, 48), (16, 48, 48)])
 def test_cluster_ca_backward_fused(shape):
     """dgrad + residual with the CALayer backward fused in, followed by a masked conv that consumes dt through the halos;
