@@ -737,7 +737,10 @@ def run_ours(args):
         e0.record()
         last = 0.0
         for i in range(args.steps):
-            loss = step.step(host_lr[i % nb], host_hr[i % nb])
+            # the next batch's H2D copy is started behind this batch's take-over and runs under this step (Runner.fit does the
+            # same with its look-ahead); every batch still crosses PCIe inside the timed region
+            nxt = (host_lr[(i + 1) % nb], host_hr[(i + 1) % nb]) if i + 1 < args.steps else None
+            loss = step.step(host_lr[i % nb], host_hr[i % nb], prefetch=nxt)
             last = loss.item()                    # D2H read of the step's result, every step
         e1.record()
         torch.cuda.synchronize()

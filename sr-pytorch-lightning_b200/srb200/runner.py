@@ -91,12 +91,27 @@ class Runner:
         (optional) is called with the device loss tensor (reading it synchronises)."""
         losses = []
         pending = []
+        def lookahead(it):
+            """(batch, next batch or None)"""
+            it = iter(it)
+            try:
+                cur = next(it)
+            except StopIteration:
+                return
+            for nxt in it:
+                yield cur, nxt
+                cur = nxt
+            yield cur, None
         for _ in range(epochs):
-            for batch in batches:
+            for batch, nxt in lookahead(batches):
                 if tuple(batch['lr'].shape) != self.lr_shape:
                     raise ValueError(f"batch shape {tuple(batch['lr'].shape)} differs from the captured {self.lr_shape}")
                 self._ensure_captured(batch)
-                loss = self.step_runner.step(batch['lr'], batch['hr'])
+                pf = None
+                if nxt is not None and not nxt['lr'].is_cuda and nxt['lr'].is_pinned() and nxt['hr'].is_pinned() \
+                        and tuple(nxt['lr'].shape) == self.lr_shape:
+                    pf = (nxt['lr'], nxt['hr'])                          # its H2D copy runs under this step
+                loss = self.step_runner.step(batch['lr'], batch['hr'], prefetch=pf)
                 self.global_step += 1
                 pending.append(loss.clone())          # the graph overwrites its loss buffer every replay
                 if on_step is not None:

@@ -128,6 +128,8 @@ class TrainStep:
                                             max_sections=int(os.environ.get("SRB200_WGRAD_OVERLAP_GROUPS", "8")),
                                             on_section_done=self._reduce_bucket if self.world > 1 and
                                             os.environ.get("SRB200_ALLREDUCE_BUCKETS", "0") not in ("", "0") else None)
+        self._stage = None          # staging buffers / copy stream of prefetch()
+        self._prefetched = None
         self._reduced = []          # [lo, hi) element ranges of flat.grad already all-reduced in this step
         self._pending = None        # (lo, hi, groups) collected for the next bucket
         # SRB200_ALLREDUCE_BUCKETS: "0" (default) = one all-reduce of the whole buffer after backward; "tail" = the gradients of the groups whose weight gradients ran on the side
@@ -261,8 +263,34 @@ class TrainStep:
     capture = prepare
 
     def load_batch(self, lr_batch, hr_batch):
+        pf = self._prefetched
+        if pf is not None and pf[0] is lr_batch and pf[1] is hr_batch:
+            # staged by prefetch() while the previous step ran: two device-to-device copies behind the copy stream's event
+            self._prefetched = None
+            torch.cuda.current_stream(self.device).wait_event(pf[2])
+            self.x.copy_(self._stage[0], non_blocking=True)
+            self.hr.copy_(self._stage[1], non_blocking=True)
+            return
         self.x.copy_(lr_batch, non_blocking=True)
         self.hr.copy_(hr_batch, non_blocking=True)
+
+    def prefetch(self, lr_batch, hr_batch):
+        """Start the host-to-device copy of the NEXT batch (pinned host tensors) on a copy stream, into staging buffers; the
+        step() that is later called with the same two tensors takes it from there.  Call it before step() of the current
+        batch: the DMA then runs under that step instead of in front of the next one (the reference gets the same from its
+        DataLoader's pin_memory + non_blocking transfers, srdata.py:514-516)."""
+        if self._stage is None:
+            self._stage = (torch.empty_like(self.x), torch.empty_like(self.hr))
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stage_free = None
+        if self._stage_free is not None:
+            self._copy_stream.wait_event(self._stage_free)      # the previous staged batch has been taken over
+        with torch.cuda.stream(self._copy_stream):
+            self._stage[0].copy_(lr_batch, non_blocking=True)
+            self._stage[1].copy_(hr_batch, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._prefetched = (lr_batch, hr_batch, ev)
 
     def run(self):
         # the step's Adam kernel rewrites the parameters without bumping tensor versions: packed copies that the
@@ -277,8 +305,16 @@ class TrainStep:
             self.launches_per_step = L.launch_count() - c0
         return self.loss
 
-    def step(self, lr_batch, hr_batch):
+    def step(self, lr_batch, hr_batch, prefetch=None):
+        """One step on (lr_batch, hr_batch).  prefetch = (lr, hr) of the NEXT batch (pinned host tensors): its host-to-device
+        copy is started on the copy stream right after this batch has been taken over and runs under this step's graph."""
+        staged = self._prefetched is not None
         self.load_batch(lr_batch, hr_batch)
+        if staged and self._prefetched is None:      # the staging buffers may be refilled once these copies have run
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record(torch.cuda.current_stream(self.device))
+        if prefetch is not None:
+            self.prefetch(prefetch[0], prefetch[1])
         return self.run()
 
     def close(self):

@@ -142,3 +142,29 @@ def test_trainstep_fp32_matches_oracle_adam(cls, kwargs):
         assert worst < 2e-4, worst
     finally:
         ts.close()
+
+
+def test_prefetched_batches_give_the_same_steps():
+    """TrainStep.step(..., prefetch=next): the next batch crosses PCIe on a copy stream under the current step and is taken
+    from the staging buffers — same losses as plain step() on the same pinned batches."""
+    import models
+    from srb200.trainer import TrainStep
+    data = [(x.pin_memory(), hr.pin_memory()) for x, hr in _batches(2, 2, 5, seed=4)]
+    out = []
+    for use_prefetch in (False, True):
+        torch.manual_seed(9)
+        m = models.EDSR(n_feats=64, n_resblocks=2, res_scale=1.0, scale_factor=2)
+        m.compute_dtype = "fp32"          # deterministic kernels: the two runs must agree to rounding of the reductions
+        ts = TrainStep(m.cuda(), (2, 3, 16, 24), 2, lr=1e-3)
+        ts.load_batch(data[0][0].cuda(), data[0][1].cuda())
+        snap = (ts.flat.flat.clone(), ts.flat.m.clone(), ts.flat.v.clone())
+        ts.prepare()
+        ts.flat.flat.copy_(snap[0]); ts.flat.m.copy_(snap[1]); ts.flat.v.copy_(snap[2]); ts.flat.step_dev.zero_()
+        losses = []
+        for i, (x, hr) in enumerate(data):
+            nxt = data[i + 1] if (use_prefetch and i + 1 < len(data)) else None
+            losses.append(ts.step(x, hr, prefetch=nxt).item())
+        out.append(losses)
+        ts.close()
+    assert all(abs(a - b) <= 1e-5 * abs(a) for a, b in zip(*out)), out
+    assert len(set(round(v, 4) for v in out[0])) > 1
