@@ -317,6 +317,35 @@ class TrainStep:
             self.prefetch(prefetch[0], prefetch[1])
         return self.run()
 
+    def step_async(self, lr_batch, hr_batch, prefetch=None) -> int:
+        """step() whose loss travels to a pinned host slot behind the step instead of being read synchronously: returns a
+        ticket for loss_of().  A loop that reads ticket i-1 after launching step i keeps one step queued on the device, so
+        the host's per-step work (launch, the read's wake-up) is hidden; at most len(ring)-1 tickets may be outstanding."""
+        self.step(lr_batch, hr_batch, prefetch=prefetch)
+        return self._post_loss()
+
+    def run_async(self) -> int:
+        """run() on the batch already in the static buffers, loss through the pinned ring (see step_async)."""
+        self.run()
+        return self._post_loss()
+
+    def _post_loss(self) -> int:
+        if getattr(self, "_loss_ring", None) is None:
+            self._loss_ring = torch.zeros(4, dtype=torch.float32).pin_memory()
+            self._loss_events = [torch.cuda.Event() for _ in range(4)]
+            self._ticket = 0
+        t = self._ticket
+        self._ticket += 1
+        self._loss_ring[t % 4: t % 4 + 1].copy_(self.loss.reshape(1), non_blocking=True)
+        self._loss_events[t % 4].record(torch.cuda.current_stream(self.device))
+        return t
+
+    def loss_of(self, ticket: int) -> float:
+        if not (self._ticket - 4 < ticket < self._ticket):
+            raise ValueError(f"ticket {ticket} is no longer (or not yet) in the loss ring")
+        self._loss_events[ticket % 4].synchronize()
+        return float(self._loss_ring[ticket % 4])
+
     def close(self):
         ops.PackTable.uninstall()
         self.flat.detach()

@@ -163,7 +163,16 @@ def test_prefetched_batches_give_the_same_steps():
         losses = []
         for i, (x, hr) in enumerate(data):
             nxt = data[i + 1] if (use_prefetch and i + 1 < len(data)) else None
-            losses.append(ts.step(x, hr, prefetch=nxt).item())
+            if use_prefetch:              # loss read one step behind the launch, through the pinned ring
+                t = ts.step_async(x, hr, prefetch=nxt)
+                if i:
+                    losses.append(ts.loss_of(t - 1))
+            else:
+                losses.append(ts.step(x, hr).item())
+        if use_prefetch:
+            losses.append(ts.loss_of(t))
+            with pytest.raises(ValueError):
+                ts.loss_of(t - 4)
         out.append(losses)
         ts.close()
     assert all(abs(a - b) <= 1e-5 * abs(a) for a, b in zip(*out)), out
