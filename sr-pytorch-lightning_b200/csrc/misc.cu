@@ -604,7 +604,87 @@ extern "C" int srb_adam_step(srb_ctx* ctx, float* param, const float* grad, floa
 // ---------------------------------------------------------------------------------------------
 // table-driven re-pack of all conv weights of a model in ONE launch (per optimizer step)
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_table_kernel(const srb_pack_item* __restrict__ table) {
+// 3x3 tensor-core packing through shared memory.  In OIHW the 64 input channels x 9 taps of one output channel are ONE
+// contiguous run of 576 floats, and that run is what both packed forms slice: the forward form takes it as (row = co,
+// K = ci), the input-gradient form as (K = co, row = ci) with the taps mirrored.  A CTA stages 32 such runs (coalesced
+// reads, converted to bf16: 36 KB) and writes 16-byte packed vectors from the staged tile.  The gather form below read one
+// float per 32-byte sector: 1 GB of sector traffic per RCAN step for 62 MB of parameters (0.10 ms).
+constexpr int kPkOuter = 32;
+constexpr int kPkPitch = 64 * 9 + 2;      // halfwords per staged run; +2 spreads the 8-run column reads over the banks
+constexpr int kPkSubElems = kPkOuter * 64 * 9;
+
+__device__ __forceinline__ uint16_t bf16_bits(float f) {
+  __nv_bfloat16 h = __float2bfloat16_rn(f);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+
+__device__ void pack_umma3_staged(const srb_pack_item& it, uint16_t* T) {
+  const bool fwd = it.mode == SRB_PACK_FWD;
+  const int Cout = it.Cout, Cin = it.Cin;
+  const int rr = it.shuffle > 1 ? it.shuffle * it.shuffle : 1;
+  const int Cp = Cout / rr;
+  const int cin_e = fwd ? Cin : Cout, cout_e = fwd ? Cout : Cin;     // K extent / rows of the packed matrix
+  const int nchunk = (cin_e + 63) / 64;
+  const int nrb = fwd ? (cout_e + kPkOuter - 1) / kPkOuter : (cout_e + 63) / 64;
+  const int nsub = fwd ? nchunk * nrb : nchunk * 2 * nrb;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint4* out = reinterpret_cast<uint4*>(it.dst);
+  for (int sb = blockIdx.x; sb < nsub; sb += gridDim.x) {
+    // staged runs: outer = output channel (forward: the packed row; input gradient: the K index), inner = 64 input channels
+    int chunk, hf = 0, outer0, inner0;
+    if (fwd) {
+      chunk = sb / nrb;
+      outer0 = (sb % nrb) * kPkOuter;
+      inner0 = chunk * 64;
+    } else {
+      chunk = sb / (2 * nrb);
+      const int rem = sb % (2 * nrb);
+      hf = rem / nrb;
+      outer0 = chunk * 64 + hf * kPkOuter;
+      inner0 = (rem % nrb) * 64;
+    }
+    const int n_inner = min(64, Cin - inner0);
+    __syncthreads();      // the previous sub-block's readers are done with T
+    for (int o = warp; o < kPkOuter; o += 8) {
+      const int oi = outer0 + o;
+      const bool valid = oi < Cout;
+      const int co = !valid ? 0 : (rr > 1 ? (oi % Cp) * rr + oi / Cp : oi);
+      const float* run = it.src + ((int64_t)co * Cin + inner0) * 9;
+      const int len = valid ? n_inner * 9 : 0;
+#pragma unroll
+      for (int e = lane; e < 576; e += 32) T[o * kPkPitch + e] = bf16_bits(e < len ? run[e] : 0.f);
+    }
+    __syncthreads();
+    if (fwd) {
+      for (int u = threadIdx.x; u < 9 * kPkOuter * 8; u += blockDim.x) {
+        const int j = u & 7, o = (u >> 3) & (kPkOuter - 1), slot = u >> 8;      // slot = kw * 3 + kh of the packed buffer
+        const int row = outer0 + o;
+        if (row >= cout_e) continue;
+        const int kw = slot / 3, kh = slot % 3;
+        const uint16_t* t = T + o * kPkPitch + (j * 8) * 9 + kh * 3 + kw;
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[q] = (uint32_t)t[(2 * q) * 9] | ((uint32_t)t[(2 * q + 1) * 9] << 16);
+        out[(((int64_t)(chunk * 3 + kw) * 3 + kh) * cout_e + row) * 8 + j] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    } else {
+      for (int u = threadIdx.x; u < 9 * 64 * 4; u += blockDim.x) {
+        const int j4 = u & 3, r = (u >> 2) & 63, slot = u >> 8;
+        const int row = inner0 + r;
+        if (row >= cout_e) continue;
+        const int kw = slot / 3, kh = slot % 3;
+        const uint16_t* t = T + (j4 * 8) * kPkPitch + r * 9 + (2 - kh) * 3 + (2 - kw);      // mirrored taps
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[q] = (uint32_t)t[(2 * q) * kPkPitch] | ((uint32_t)t[(2 * q + 1) * kPkPitch] << 16);
+        out[(((int64_t)(chunk * 3 + kw) * 3 + kh) * cout_e + row) * 8 + hf * 4 + j4] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) pack_table_kernel(const srb_pack_item* __restrict__ table) {
+  __shared__ uint16_t stage[kPkOuter * kPkPitch];
   const srb_pack_item it = table[blockIdx.y];
   const int k = it.ksize;
   if (k == 0) {  // bias
@@ -614,6 +694,10 @@ __global__ void pack_table_kernel(const srb_pack_item* __restrict__ table) {
   }
   const int Cout = it.Cout, Cin = it.Cin;
   const int rr = it.shuffle > 1 ? it.shuffle * it.shuffle : 1;
+  if (it.packing == SRB_PACK_UMMA && k == 3) {
+    pack_umma3_staged(it, stage);
+    return;
+  }
   if (it.packing == SRB_PACK_UMMA) {
     // Output-centric: a thread produces 8 consecutive bf16 of the packed buffer (one 16-byte store,
     // fully coalesced) and gathers its 8 sources — strided fp32 reads that the nine taps / 64 channels
@@ -675,6 +759,7 @@ extern "C" int srb_pack_table(srb_ctx* ctx, const srb_pack_item* table_dev, int 
   // grid.x is sized for a TYPICAL item (the caller passes the median filter size): every path of the kernel is a
   // grid-stride loop, so larger filters take more trips; one 256-thread CTA per 2048 elements = one 16-byte packed
   // vector per thread.  Sizing it for the largest filter launched 105 k CTAs per RCAN step, most without work.
+  // (A 3x3 tensor-core item takes one CTA per 32 x 64 x 9 elements: pack_umma3_staged; its surplus CTAs exit at once.)
   int bx = srb_cdiv(max_elems, 256 * 8);
   if (bx < 1) bx = 1;
   if (bx > 64) bx = 64;

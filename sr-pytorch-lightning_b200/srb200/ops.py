@@ -154,9 +154,16 @@ class PackTable:
         assert dt.itemsize == C.sizeof(L.PackItem)
         arr = np.array(rows, dtype=dt)
         self.n = len(rows)
-        sizes = sorted(r[2] * r[3] * r[4] * r[4] for r in rows if r[4] > 0)
-        # grid rows are sized for the median filter (srb_pack_table): larger ones loop
-        self.max_elems = sizes[len(sizes) // 2] if sizes else max_elems
+        # grid rows are sized for the median item (srb_pack_table: one CTA per 2048 of max_elems; larger items loop).  A 3x3
+        # tensor-core item wants one CTA per 32 x 64 x 9 staged elements (misc.cu pack_umma3_staged), the others one per 2048.
+        def ctas(r):
+            cout, cin, k, packing, mode = r[2], r[3], r[4], r[5], r[6]
+            if packing == L.PACK_UMMA and k == 3:
+                kdim, rows_ = (cin, cout) if mode == L.PACK_FWD else (cout, cin)
+                return -(-kdim // 64) * (-(-rows_ // 32) if mode == L.PACK_FWD else 2 * -(-rows_ // 64))
+            return -(-(cout * cin * k * k) // 2048)
+        demand = sorted(ctas(r) for r in rows if r[4] > 0)
+        self.max_elems = 2048 * demand[len(demand) // 2] if demand else max_elems
         self.table = torch.from_numpy(arr.view(np.uint8).copy()).to(device)
         self.device = device
 

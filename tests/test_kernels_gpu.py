@@ -511,7 +511,8 @@ def test_deferred_bias_grads_share_one_launch():
 
 
 @pytest.mark.parametrize("shape", [(64, 64, 3), (256, 64, 3), (64, 576, 1), (64, 40, 3), (3, 64, 3), (64, 3, 3), (128, 192, 3), (256, 256, 3)])
-def test_pack_table_matches_pack_weight(shape):
+@pytest.mark.parametrize("grid_elems", [None, 2048])
+def test_pack_table_matches_pack_weight(shape, grid_elems):
     """srb_pack_table (one launch re-packing many weights, used once per optimizer step) must write
     exactly the bytes srb_pack_weight writes, for every packing / mode / shuffle, including the
     zero-padded partial 64-channel chunk."""
@@ -527,13 +528,14 @@ def test_pack_table_matches_pack_weight(shape):
         for mode in (L.PACK_FWD, L.PACK_DGRAD):
             for shuffle in ((0, 2) if cout % 4 == 0 else (0,)):
                 want = ops.pack_weight(w, packing, mode, shuffle)
-                got = torch.zeros_like(want)       # UMMA padding of a partial chunk stays as first packed (zeros)
+                got = torch.ones_like(want)        # every byte is rewritten, the zero padding of a partial chunk included
                 rows.append((w.data_ptr(), got.data_ptr(), cout, cin, k, packing, mode, shuffle))
                 keep.append((want, got, packing, mode, shuffle))
     dt = np.dtype([("src", "<u8"), ("dst", "<u8"), ("Cout", "<i4"), ("Cin", "<i4"), ("ksize", "<i4"),
                    ("packing", "<i4"), ("mode", "<i4"), ("shuffle", "<i4")])
     table = torch.from_numpy(np.array(rows, dtype=dt).view(np.uint8).copy()).to(dev)
-    L.check(L.load().srb_pack_table(C.c_void_p(L.ctx(0)), C.c_void_p(table.data_ptr()), len(rows), w.numel(),
+    # grid_elems = 2048: one CTA per item, every path loops over its whole item
+    L.check(L.load().srb_pack_table(C.c_void_p(L.ctx(0)), C.c_void_p(table.data_ptr()), len(rows), grid_elems or w.numel(),
                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)), "srb_pack_table")
     torch.cuda.synchronize()
     for want, got, packing, mode, shuffle in keep:
