@@ -45,6 +45,18 @@ constexpr int kWinBytes1 = 23 * 1024;            // 18 x 10 x 128 = 23040, padde
 constexpr int kWinTx1 = (kTH + 2) * kPW * 128;
 constexpr int kStageBytes1 = kWinBytes1 + kGBytes;
 constexpr int kStages1 = 5;
+// N = 128 variant of the single-window form (default; SRB200_WGRAD_N128=0 selects the N = 64 form above): the gy tile is
+// loaded with ONE extra row on top (17 x 8 pixels) and used as two N blocks, [gy shifted up one row | gy], the second simply
+// 1024 bytes (one tile row) further (the descriptor's leading-dimension offset, as for the two stacked taps of A).  With
+// A = taps (0,kw) | (1,kw) one 128 x 128 accumulator per kw then holds
+//     lanes 0-63,  columns 64-127: tap (0,kw)        lanes 64-127, columns 64-127: tap (1,kw)
+//     lanes 64-127, columns 0-63 : tap (2,kw)        lanes 0-63,  columns 0-63  : tap (1,kw) again, discarded
+// (x[p + 1 row] * gy[p - 1 row + 1 row]: shifting BOTH operands of a tap by one row re-tiles the same pixel sum; the row it
+// drops at the bottom edge multiplies the zero padding row of x, the row it adds at the top is TMA's zero fill of gy).
+// 24 MMAs of 128 x 128 x 16 per tile instead of 40 of 128 x 64 x 16: an N = 64 MMA is bound by the shared-memory port
+// (48 cycles for 32 of math, profiles/r01_hw_probes.txt), N = 128 by the tensor pipe (64 for 64).
+constexpr int kGBytes2 = (kTH + 1) * kTW * 128;  // 17 rows
+constexpr int kStageBytes2 = kWinBytes1 + kGBytes2;
 constexpr int kMaxBlocks = 74;      // blocks per launch (kernel-parameter space: 74 x 320 B < 32 KB)
 constexpr uint32_t kTmemCols = 512; // 5 accumulators x 64 columns -> next power of two
 
@@ -67,12 +79,14 @@ struct alignas(64) WgradBlock {
 struct WgradParams {
   WgradBlock blk[kMaxBlocks];
   int nblocks;
+  int scatter;      // N = 128 form only: 1 = write dW straight from the TMEM lanes (SRB200_WGRAD_SCATTER=1, for A/B runs)
 };
 
-template <bool OW>
+template <int V>      // 0: three kw-shifted windows (also 1x1 layers), 1: single window, 2: single window, N = 128
 __global__ void __launch_bounds__(kThreads, 1) wgrad_umma_kernel(const __grid_constant__ WgradParams P) {
+  constexpr bool OW = V >= 1, N128 = V == 2;
   constexpr int kStages = OW ? kStages1 : ::kStages;
-  constexpr int kStageBytes = OW ? kStageBytes1 : ::kStageBytes;
+  constexpr int kStageBytes = N128 ? kStageBytes2 : (OW ? kStageBytes1 : ::kStageBytes);
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kStages];
   __shared__ uint64_t empty_bar[kStages];
@@ -118,9 +132,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_umma_kernel(const __grid_co
         ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
         const uint32_t base = ring + (uint32_t)s * kStageBytes;
         if constexpr (OW) {
-          ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(kWinTx1 + kGBytes));
+          ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(kWinTx1 + (N128 ? kGBytes2 : kGBytes)));
           ptx::tma_load_4d(base, &B.tmX, &full_bar[s], B.xc0, w0 - 1, h0 - 1, n);
-          ptx::tma_load_4d(base + kWinBytes1, &B.tmG, &full_bar[s], B.gc0, w0, h0, n);
+          ptx::tma_load_4d(base + kWinBytes1, &B.tmG, &full_bar[s], B.gc0, w0, N128 ? h0 - 1 : h0, n);
         } else {
           ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(B.k1 ? kABytes + kGBytes : kStageBytes));
 #pragma unroll
@@ -148,6 +162,19 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_umma_kernel(const __grid_co
         constexpr uint32_t hi = ptx::smem_desc_hi_sw128(1024u);
         const uint32_t g_lo = ptx::smem_desc_lo(gbase, 1024u);
         const uint32_t acc_flag = (uint32_t)(it != 0);
+        if constexpr (N128) {
+          constexpr uint32_t idesc2 = ptx::idesc_bf16_f32(128, 128, 1, 1);
+          constexpr uint32_t hi1 = ptx::smem_desc_hi_sw128((uint32_t)kPW * 128u);
+          const uint32_t g2_lo = ptx::smem_desc_lo(gbase, 1024u);      // second N block: the unshifted tile, one row further
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            const uint32_t a_lo = ptx::smem_desc_lo(base + (uint32_t)(a * 128), (uint32_t)kPW * 128u);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              ptx::umma_bf16_lohi(tmem_acc + (uint32_t)a * 128u, a_lo + j * (2u * kPW * 128u / 16u), hi1, g2_lo + j * 128u, hi,
+                                  idesc2, j != 0 ? 1u : acc_flag);
+          }
+        } else
 #pragma unroll
         for (int a = 0; a < 5; ++a) {
           if (B.k1 && a != 1) continue;   // 1x1: the centre tap is the upper half of accumulator 1
@@ -182,6 +209,69 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_umma_kernel(const __grid_co
     const int Cp = B.Cout / rr;
     ptx::mbar_wait(&tmem_full_bar, 0);
     ptx::tc_fence_after();
+    if constexpr (N128) {
+      if (!P.scatter) {
+        // A TMEM lane holds one (tap, ci) against 64 co: written straight to OIHW that is one float per 32-byte sector (and
+        // one red.global per float when the block's pixels are split over CTAs: ~40 us per launch).  Instead the block is
+        // staged as [co][ci][9 taps] fp32 in the (now idle) operand ring — for one co that is the layer's contiguous run of
+        // 64 x 9 floats — and written out / added with consecutive threads on consecutive floats.
+        float* stg = reinterpret_cast<float*>(smem_raw + (ring - ptx::smem_u32(smem_raw)));
+#pragma unroll 1
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll 1
+          for (int c0 = half ? 0 : 64; c0 < 128; c0 += 32) {
+            const int tap = (c0 < 64 ? 2 : half) * 3 + a;
+            uint32_t acc[32];
+            ptx::tmem_ld_32x32b_x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 128 + c0), acc);
+            ptx::tmem_ld_wait();
+            float* s0 = stg + ((c0 & 63) * 64 + (row & 63)) * 9 + tap;      // lanes: stride 9 floats, conflict-free
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s0[j * 576] = __uint_as_float(acc[j]) * B.alpha;
+          }
+        }
+        ptx::named_bar_sync(1, 128);
+        const int t = (int)threadIdx.x - 64;
+        const int run = min(64, B.Cin - B.ci0) * 9;
+#pragma unroll 1
+        for (int c = 0; c < 64; ++c) {
+          const int cop = B.co0 + c;
+          if (cop >= B.Cout) break;
+          const int co = rr > 1 ? (cop % Cp) * rr + cop / Cp : cop;
+          float* dst = B.dw + ((int64_t)co * B.Cin + B.ci0) * 9;
+          const float* src = stg + c * 576;
+          if (S > 1) {
+            for (int e = t; e < run; e += 128) atomicAdd(dst + e, src[e]);
+          } else if (B.rmw) {
+            for (int e = t; e < run; e += 128) dst[e] += src[e];
+          } else {
+            for (int e = t; e < run; e += 128) dst[e] = src[e];
+          }
+        }
+      } else
+#pragma unroll 1
+      for (int a = 0; a < 3; ++a) {          // a = kw
+#pragma unroll 1
+        for (int c0 = half ? 0 : 64; c0 < 128; c0 += 32) {      // lanes 0-63 own nothing in the shifted columns
+          const int kh = c0 < 64 ? 2 : half;
+          uint32_t acc[32];
+          ptx::tmem_ld_32x32b_x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 128 + c0), acc);
+          ptx::tmem_ld_wait();
+          if (ci < B.Cin) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int cop = B.co0 + (c0 & 63) + j;
+              if (cop >= B.Cout) continue;
+              const int co = rr > 1 ? (cop % Cp) * rr + cop / Cp : cop;
+              float* dst = B.dw + (((int64_t)co * B.Cin + ci) * 3 + kh) * 3 + a;
+              const float v = __uint_as_float(acc[j]) * B.alpha;
+              if (S > 1) atomicAdd(dst, v);
+              else if (B.rmw) *dst += v;
+              else *dst = v;
+            }
+          }
+        }
+      }
+    } else
 #pragma unroll 1
     for (int a = 0; a < 5; ++a) {
       if (B.k1 && a != 1) continue;
@@ -324,15 +414,22 @@ int srb_wgrad_umma_batched(srb_ctx* ctx, const srb_wgrad_desc* descs, const void
     const char* e = getenv("SRB200_WGRAD_ONEWIN");
     return !(e && e[0] == '0');
   }();
+  static const bool n128_enabled = [] {
+    const char* e = getenv("SRB200_WGRAD_N128");
+    return !(e && e[0] == '0');
+  }();
   bool one_win = one_win_enabled;
   for (int i = 0; i < n_items; ++i)
     if (descs[i].ksize == 1) one_win = false;
-  const size_t smem = (one_win ? (size_t)kStages1 * kStageBytes1 : (size_t)kStages * kStageBytes) + 1024;
+  const bool n128 = one_win && n128_enabled;
+  const size_t smem = (n128 ? (size_t)kStages1 * kStageBytes2 : one_win ? (size_t)kStages1 * kStageBytes1 : (size_t)kStages * kStageBytes) + 1024;
   if (!attr_set) {
-    SRB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SRB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)((size_t)kStages * kStageBytes + 1024)));
-    SRB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SRB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)((size_t)kStages1 * kStageBytes1 + 1024)));
+    SRB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)((size_t)kStages1 * kStageBytes2 + 1024)));
     attr_set = true;
   }
   std::vector<WgradBlock> blocks;
@@ -341,7 +438,7 @@ int srb_wgrad_umma_batched(srb_ctx* ctx, const srb_wgrad_desc* descs, const void
     CUtensorMap tmX, tmG;  // one pair per layer; its 64x64 blocks differ by channel coordinates only
     int rc = encode_act_map(ctx, &tmX, xs[i], d.N, d.H, d.W, d.x_cs, d.x_co + d.Cin, kTH + 2, one_win ? kPW : kTW);
     if (rc) return rc;
-    rc = encode_act_map(ctx, &tmG, gys[i], d.N, d.H, d.W, d.g_cs, d.g_co + d.Cout, kTH);
+    rc = encode_act_map(ctx, &tmG, gys[i], d.N, d.H, d.W, d.g_cs, d.g_co + d.Cout, n128 ? kTH + 1 : kTH);
     if (rc) return rc;
     const int tiles_w = srb_cdiv(d.W, kTW), tiles_h = srb_cdiv(d.H, kTH);
     for (int cb = 0; cb < srb_cdiv(d.Cin, 64); ++cb) {
@@ -383,6 +480,11 @@ int srb_wgrad_umma_batched(srb_ctx* ctx, const srb_wgrad_desc* descs, const void
     for (auto& B : blocks) B.rmw = 1;
   }
   WgradParams* P = new WgradParams();
+  static const int scatter = [] {
+    const char* e = getenv("SRB200_WGRAD_SCATTER");
+    return (e && e[0] == '1') ? 1 : 0;
+  }();
+  P->scatter = scatter;
   int rc = 0;
   for (size_t li = 0; li < launch_start.size() && rc == 0; ++li) {
     const int b0 = launch_start[li];
@@ -390,8 +492,9 @@ int srb_wgrad_umma_batched(srb_ctx* ctx, const srb_wgrad_desc* descs, const void
     for (int b = 0; b < nb; ++b) P->blk[b] = blocks[b0 + b];
     P->nblocks = nb;
     const int ctas = P->blk[nb - 1].cta0 + P->blk[nb - 1].S;
-    if (one_win) wgrad_umma_kernel<true><<<ctas, kThreads, smem, st>>>(*P);
-    else wgrad_umma_kernel<false><<<ctas, kThreads, smem, st>>>(*P);
+    if (n128) wgrad_umma_kernel<2><<<ctas, kThreads, smem, st>>>(*P);
+    else if (one_win) wgrad_umma_kernel<1><<<ctas, kThreads, smem, st>>>(*P);
+    else wgrad_umma_kernel<0><<<ctas, kThreads, smem, st>>>(*P);
     __atomic_fetch_add(&g_srb_launches, 1ull, __ATOMIC_RELAXED);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -366,7 +366,7 @@ class WgradOverlap:
     Reference behaviour replaced: autograd runs each layer's weight gradient right behind its input gradient on the one
     stream; the result is the same sum, accumulated into the same flat gradient buffer."""
 
-    def __init__(self, device, sm_budget: int = 52, max_sections: int = 8, on_section_done=None):
+    def __init__(self, device, sm_budget: int = 52, max_sections: int = 9, on_section_done=None):
         self.device = device
         # on_section_done(lo_ptr, hi_ptr): called on the side stream behind a section's launches with the address range of the
         # gradient buffers they wrote (data-parallel training: all-reduce that bucket under the following chains)

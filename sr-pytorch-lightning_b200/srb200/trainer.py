@@ -125,7 +125,7 @@ class TrainStep:
                 and os.environ.get("SRB200_CHAIN_CLUSTER", "1") not in ("0",) \
                 and os.environ.get("SRB200_NO_CHAIN", "0") in ("", "0"):
             self.overlap = ops.WgradOverlap(dev, sm_budget=int(os.environ.get("SRB200_WGRAD_OVERLAP_SMS", "52")),
-                                            max_sections=int(os.environ.get("SRB200_WGRAD_OVERLAP_GROUPS", "8")),
+                                            max_sections=int(os.environ.get("SRB200_WGRAD_OVERLAP_GROUPS", "9")),
                                             on_section_done=self._reduce_bucket if self.world > 1 and
                                             os.environ.get("SRB200_ALLREDUCE_BUCKETS", "0") not in ("", "0") else None)
         self._stage = None          # staging buffers / copy stream of prefetch()
