@@ -26,7 +26,7 @@ lib = L.load()
 
 
 def run():
-    L.check(lib.srb_pack_table(C.c_void_p(L.ctx(0)), C.c_void_p(table.data_ptr()), len(rows), 64 * 64 * 9,
+    L.check(lib.srb_pack_table(C.c_void_p(L.ctx(0)), C.c_void_p(table.data_ptr()), len(rows), int(os.environ.get("PACK_GRID_ELEMS", 64 * 64 * 9)),
                                C.c_void_p(torch.cuda.current_stream().cuda_stream)), "srb_pack_table")
 
 

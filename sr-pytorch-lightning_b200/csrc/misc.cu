@@ -645,14 +645,23 @@ __device__ void pack_umma3_staged(const srb_pack_item& it, uint16_t* T) {
     }
     const int n_inner = min(64, Cin - inner0);
     __syncthreads();      // the previous sub-block's readers are done with T
-    for (int o = warp; o < kPkOuter; o += 8) {
-      const int oi = outer0 + o;
-      const bool valid = oi < Cout;
-      const int co = !valid ? 0 : (rr > 1 ? (oi % Cp) * rr + oi / Cp : oi);
-      const float* run = it.src + ((int64_t)co * Cin + inner0) * 9;
-      const int len = valid ? n_inner * 9 : 0;
+    {
+      // the warp's 4 runs: all 72 loads of a lane are issued before the first conversion / shared-memory store
+      float v[kPkOuter / 8][18];
 #pragma unroll
-      for (int e = lane; e < 576; e += 32) T[o * kPkPitch + e] = bf16_bits(e < len ? run[e] : 0.f);
+      for (int i = 0; i < kPkOuter / 8; ++i) {
+        const int oi = outer0 + warp + 8 * i;
+        const bool valid = oi < Cout;
+        const int co = !valid ? 0 : (rr > 1 ? (oi % Cp) * rr + oi / Cp : oi);
+        const float* run = it.src + ((int64_t)co * Cin + inner0) * 9;
+        const int len = valid ? n_inner * 9 : 0;
+#pragma unroll
+        for (int k = 0; k < 18; ++k) v[i][k] = lane + 32 * k < len ? __ldg(run + lane + 32 * k) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < kPkOuter / 8; ++i)
+#pragma unroll
+        for (int k = 0; k < 18; ++k) T[(warp + 8 * i) * kPkPitch + lane + 32 * k] = bf16_bits(v[i][k]);
     }
     __syncthreads();
     if (fwd) {
@@ -683,7 +692,7 @@ __device__ void pack_umma3_staged(const srb_pack_item& it, uint16_t* T) {
   }
 }
 
-__global__ void __launch_bounds__(256) pack_table_kernel(const srb_pack_item* __restrict__ table) {
+__global__ void __launch_bounds__(256) pack_table_kernel(const srb_pack_item* __restrict__ table, int staged) {
   __shared__ uint16_t stage[kPkOuter * kPkPitch];
   const srb_pack_item it = table[blockIdx.y];
   const int k = it.ksize;
@@ -694,7 +703,7 @@ __global__ void __launch_bounds__(256) pack_table_kernel(const srb_pack_item* __
   }
   const int Cout = it.Cout, Cin = it.Cin;
   const int rr = it.shuffle > 1 ? it.shuffle * it.shuffle : 1;
-  if (it.packing == SRB_PACK_UMMA && k == 3) {
+  if (it.packing == SRB_PACK_UMMA && k == 3 && staged) {
     pack_umma3_staged(it, stage);
     return;
   }
@@ -763,7 +772,11 @@ extern "C" int srb_pack_table(srb_ctx* ctx, const srb_pack_item* table_dev, int 
   int bx = srb_cdiv(max_elems, 256 * 8);
   if (bx < 1) bx = 1;
   if (bx > 64) bx = 64;
-  pack_table_kernel<<<dim3(bx, n), 256, 0, S(stream)>>>(table_dev);
+  static const int staged = [] {      // SRB200_PACK_STAGED=0: the gather form for every item (A/B runs)
+    const char* e = getenv("SRB200_PACK_STAGED");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  pack_table_kernel<<<dim3(bx, n), 256, 0, S(stream)>>>(table_dev, staged);
   SRB_LAUNCH_CHECK();
   return 0;
 }

@@ -239,7 +239,22 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_umma_kernel(const __grid_co
           const int co = rr > 1 ? (cop % Cp) * rr + cop / Cp : cop;
           float* dst = B.dw + ((int64_t)co * B.Cin + B.ci0) * 9;
           const float* src = stg + c * 576;
-          if (S > 1) {
+          if (((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)(run * 4)) & 15) == 0) {      // 16-byte runs: vector red / stores
+            float4* dst4 = reinterpret_cast<float4*>(dst);
+            const float4* src4 = reinterpret_cast<const float4*>(src);
+            if (S > 1) {
+              for (int e = t; e < run / 4; e += 128) atomicAdd(dst4 + e, src4[e]);
+            } else if (B.rmw) {
+              for (int e = t; e < run / 4; e += 128) {
+                float4 d = dst4[e];
+                const float4 v = src4[e];
+                d.x += v.x; d.y += v.y; d.z += v.z; d.w += v.w;
+                dst4[e] = d;
+              }
+            } else {
+              for (int e = t; e < run / 4; e += 128) dst4[e] = src4[e];
+            }
+          } else if (S > 1) {
             for (int e = t; e < run; e += 128) atomicAdd(dst + e, src[e]);
           } else if (B.rmw) {
             for (int e = t; e < run; e += 128) dst[e] += src[e];
