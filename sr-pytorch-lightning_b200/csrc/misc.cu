@@ -557,16 +557,36 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   float bc2 = 1.f - powf(b2, (float)step);
   float step_size = lr / bc1;
   float inv_sqrt_bc2 = rsqrtf(bc2);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float gi = g[i] * gscale;
-    float pi = p[i];
+  auto update = [&](float& pi, float gi, float& mi, float& vi) {
+    gi *= gscale;
     if (wd != 0.f) gi += wd * pi;
-    float mi = b1 * m[i] + (1.f - b1) * gi;
-    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    mi = b1 * mi + (1.f - b1) * gi;
+    vi = b2 * vi + (1.f - b2) * gi * gi;
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    pi = pi - step_size * (mi / denom);
+  };
+  // 16-byte lanes over the aligned body (the flat buffers of srb200.trainer.FlatParams are), scalars for the rest
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  const int64_t n4 = vec ? n / 4 : 0;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < n4; i += nthr) {
+    float4 pv = reinterpret_cast<float4*>(p)[i], mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    update(pv.x, gv.x, mv.x, vv.x);
+    update(pv.y, gv.y, mv.y, vv.y);
+    update(pv.z, gv.z, mv.z, vv.z);
+    update(pv.w, gv.w, mv.w, vv.w);
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    reinterpret_cast<float4*>(p)[i] = pv;
+  }
+  for (int64_t i = n4 * 4 + tid; i < n; i += nthr) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    update(pi, g[i], mi, vi);
     m[i] = mi;
     v[i] = vi;
-    float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
-    p[i] = pi - step_size * (mi / denom);
+    p[i] = pi;
   }
 }
 

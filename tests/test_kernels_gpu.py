@@ -348,23 +348,26 @@ def test_l1_loss_and_adam():
     torch.cuda.synchronize()
     assert abs(loss.item() - ref.item()) < 1e-6
     assert _rel(grad, srd.grad)[1] < 1e-6
-    # Adam against torch.optim.Adam for 3 steps
-    p0 = torch.randn(1000, generator=g)
-    p_ref = p0.clone().requires_grad_(True)
-    opt = torch.optim.Adam([p_ref], lr=1e-3)
-    p = p0.to(dev).clone()
-    m = torch.zeros_like(p)
-    v = torch.zeros_like(p)
-    step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
-    for step in range(1, 4):
-        gr = torch.randn(1000, generator=g)
-        p_ref.grad = gr.clone()
-        opt.step()
-        ops.inc_counter(step_dev)
-        ops.adam_step(p, (gr * 4).to(dev), m, v, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
-                      step=0, step_dev=step_dev, grad_scale=0.25)
-    torch.cuda.synchronize()
-    assert _rel(p, p_ref.detach())[1] < 1e-6
+    # Adam against torch.optim.Adam for 3 steps: 16-byte lanes (n = 1000), lanes + scalar tail (1003), and a parameter
+    # slice that is not 16-byte aligned (all-scalar path)
+    for n, off in ((1000, 0), (1003, 0), (1001, 1)):
+        p0 = torch.randn(n, generator=g)
+        p_ref = p0.clone().requires_grad_(True)
+        opt = torch.optim.Adam([p_ref], lr=1e-3)
+        p = torch.zeros(n + 4, device=dev)[off:off + n]
+        p.copy_(p0)
+        m = torch.zeros_like(p)
+        v = torch.zeros_like(p)
+        step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        for step in range(1, 4):
+            gr = torch.randn(n, generator=g)
+            p_ref.grad = gr.clone()
+            opt.step()
+            ops.inc_counter(step_dev)
+            ops.adam_step(p, (gr * 4).to(dev), m, v, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
+                          step=0, step_dev=step_dev, grad_scale=0.25)
+        torch.cuda.synchronize()
+        assert _rel(p, p_ref.detach())[1] < 1e-6, (n, off)
 
 
 def test_errors_are_reported_not_thrown():
