@@ -434,8 +434,29 @@ int srb_wgrad_umma_batched(srb_ctx* ctx, const srb_wgrad_desc* descs, const void
     return !(e && e[0] == '0');
   }();
   bool one_win = one_win_enabled;
+  int n_k1 = 0;
   for (int i = 0; i < n_items; ++i)
-    if (descs[i].ksize == 1) one_win = false;
+    if (descs[i].ksize == 1) ++n_k1;
+  if (n_k1 > 0 && n_k1 < n_items && one_win_enabled) {
+    // a mixed batch (RDN: dense 3x3 layers + 1x1 LFF / GFF): the 3x3 layers take the single-window N = 128 form in their own
+    // launches, the 1x1 layers the three-window form (which loads only their centre window)
+    for (int pass = 0; pass < 2; ++pass) {
+      std::vector<srb_wgrad_desc> d2;
+      std::vector<const void*> x2, g2;
+      std::vector<float*> w2;
+      for (int i = 0; i < n_items; ++i)
+        if ((descs[i].ksize == 1) == (pass == 1)) {
+          d2.push_back(descs[i]);
+          x2.push_back(xs[i]);
+          g2.push_back(gys[i]);
+          w2.push_back(dws[i]);
+        }
+      const int rc = srb_wgrad_umma_batched(ctx, d2.data(), x2.data(), g2.data(), w2.data(), (int)d2.size(), st);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  if (n_k1 > 0) one_win = false;
   const bool n128 = one_win && n128_enabled;
   const size_t smem = (n128 ? (size_t)kStages1 * kStageBytes2 : one_win ? (size_t)kStages1 * kStageBytes1 : (size_t)kStages * kStageBytes) + 1024;
   if (!attr_set) {

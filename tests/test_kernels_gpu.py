@@ -474,6 +474,31 @@ def test_conv_wgrad_batched_deferred():
         assert _rel(dw, rw)[0] < 1e-5 and _rel(db, rb)[0] < 1e-5
 
 
+def test_deferred_wgrads_mixed_1x1_and_3x3_batch():
+    """A deferred batch that mixes 3x3 and 1x1 layers (RDN: dense layers + LFF / GFF, rdn.py:24-40,59-72) is split by kernel
+    size — single-window N = 128 launches for the 3x3 layers, three-window launches for the 1x1 ones — and must give the
+    gradients of the per-layer calls and of torch's conv2d weight gradient."""
+    from srb200 import ops
+    g = torch.Generator().manual_seed(12)
+    dev = _dev()
+    layers = []
+    for cin, cout, k, hw in [(64, 64, 3, 32), (192, 64, 1, 32), (128, 64, 3, 32), (64, 64, 1, 24), (64, 64, 3, 24)]:
+        x = torch.randn(2, hw, hw, cin, generator=g).to(torch.bfloat16).to(dev)
+        gy = torch.randn(2, hw, hw, cout, generator=g).to(torch.bfloat16).to(dev)
+        layers.append((x, gy, cin, cout, k))
+    got = []
+    with ops.deferred_wgrads():
+        for x, gy, cin, cout, k in layers:
+            dw = torch.full((cout, cin, k, k), 9.0, device=dev)
+            ops.conv_wgrad(x, 0, cin, gy, 0, cout, k, dw, None)
+            got.append(dw)
+    torch.cuda.synchronize()
+    for (x, gy, cin, cout, k), dw in zip(layers, got):
+        want = torch.nn.grad.conv2d_weight(x.permute(0, 3, 1, 2).double(), (cout, cin, k, k), gy.permute(0, 3, 1, 2).double(),
+                                           padding=k // 2)
+        assert _rel(dw, want)[0] < 1e-5, (cin, cout, k)
+
+
 def test_deferred_bias_grads_share_one_launch():
     """Bias gradients of a deferred batch go through colsum_batched_kernel (one launch): channel
     slices, the un-shuffled (i,j,c') channel order of PixelShuffle convs, accumulate and alpha,
