@@ -476,7 +476,10 @@ def wgrad_overlap_adopt():
     if ov is None or not _wq.active or ov.adopted or not _wq.items or ov.pending is not None:
         return
     import os
-    if os.environ.get("SRB200_WGRAD_ADOPT", "0") in ("", "0"):      # measured neutral (N=1: 7.48 vs 7.51 ms, N=2: 7.64 vs 7.69): off
+    # Neutral while the side stream was as long as the chain stream (N = 64 weight-gradient kernel: 7.48 vs 7.51 ms); with the
+    # N = 128 kernel the side stream has ~110 us of slack per group and this takes the tail / up-sampling / head weight and bias
+    # gradients off the end of the step: 7.22 -> 7.14 ms.  SRB200_WGRAD_ADOPT=0 turns it off.
+    if os.environ.get("SRB200_WGRAD_ADOPT", "1") in ("", "0"):
         return
     ov.adopted = True
     q = _WgradQueue()
